@@ -1,0 +1,184 @@
+// profiles/microbench/intbench.cu -- integer-pipe throughput probe for B200 (sm_100a).
+//
+// MEASURED_PEAKS.json only records HBM and bf16 tensor peaks; the Viterbi ACS kernel is
+// bound by the integer ALU / issue rate, so the roofline denominator P_int has to be
+// measured on the box.  Each test runs UNROLL independent
+// dependency chains per thread of one instruction class (or a mix), on every SM at
+// full occupancy, and reports lane-ops/s and lane-ops per SM per clock.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o intbench intbench.cu
+//   ./intbench [iters]            -> one JSON object per line
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#define CK(x)                                                                      \
+    do {                                                                           \
+        cudaError_t e_ = (x);                                                      \
+        if (e_ != cudaSuccess) {                                                   \
+            fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(1);                                                               \
+        }                                                                          \
+    } while (0)
+
+constexpr int CHAINS = 8;
+
+enum Op {
+    OP_IADD,       // add.u32 (ptxas picks IADD3 / IMAD.IADD)
+    OP_LOP3,       // 3-input logic
+    OP_IMAD,       // mad.lo
+    OP_SHF,        // funnel shift
+    OP_PRMT,       // byte permute
+    OP_MNMX32,     // min.u32
+    OP_VIADD16,    // add.u16x2           (VIADD.16x2?)
+    OP_VMNMX16,    // min.u16x2           (VIMNMX.U16x2)
+    OP_VMNMX3_16,  // min3 u16x2          (VIMNMX3.U16x2)
+    OP_VADDMNMX16, // min(a+b,c) u16x2    (VIADDMNMX.U16x2)
+    OP_VADDMNMX32, // min(a+b,c) u32      (VIADDMNMX.U32)
+    OP_MIX_IADD_LOP,      // alternate IADD / LOP3
+    OP_MIX_VADDMNMX_IMAD, // alternate VIADDMNMX / IMAD
+    OP_MIX_VADDMNMX_IADD, // alternate VIADDMNMX / IADD3 (a+b+c form)
+    OP_MIX_VADDMNMX_LOP,  // alternate VIADDMNMX / LOP3
+    OP_ACS_CORE,          // the 3-op ACS body: t=min(B+mm,255); n=min(A+m,t); d=n+K-t
+    OP_SHFL,
+    OP_BALLOT,
+    OP_COUNT
+};
+
+static const char* op_name[OP_COUNT] = {
+    "iadd", "lop3", "imad", "shf", "prmt", "mnmx_u32", "viadd_16x2", "vimnmx_u16x2", "vimnmx3_u16x2",
+    "viaddmnmx_u16x2", "viaddmnmx_u32", "mix_iadd_lop3", "mix_viaddmnmx_imad", "mix_viaddmnmx_iadd3",
+    "mix_viaddmnmx_lop3", "acs_core_3op", "shfl_xor", "ballot"};
+// SASS instructions per chain-iteration (ptxas fuses two dependent add/min steps into one
+// IADD3 / VIMNMX3, hence 0.5 for those three)
+static const double op_count[OP_COUNT] = {0.5, 1, 1, 1, 1, 0.5, 1, 0.5, 1, 1, 1, 2, 2, 2, 2, 3, 1, 3};
+
+template <int OP>
+__device__ __forceinline__ uint32_t step(uint32_t x, uint32_t a, uint32_t b) {
+    // asm volatile keeps nvcc from folding the repeated chain step algebraically
+    if (OP == OP_IADD) { asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(a)); return x; }
+    if (OP == OP_LOP3) { asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x) : "r"(a), "r"(b)); return x; }
+    if (OP == OP_IMAD) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)); return x; }
+    if (OP == OP_SHF) return __funnelshift_l(x, a, 7);
+    if (OP == OP_PRMT) return __byte_perm(x, a, 0x2103);
+    if (OP == OP_MNMX32) { asm volatile("min.u32 %0, %0, %1;" : "+r"(x) : "r"(a)); return x; }
+    if (OP == OP_VIADD16) return __vadd2(x, a);
+    if (OP == OP_VMNMX16) { asm volatile("min.u16x2 %0, %0, %1;" : "+r"(x) : "r"(a)); return x; }
+    if (OP == OP_VMNMX3_16) return __vimin3_u16x2(x, a, b);
+    if (OP == OP_VADDMNMX16) return __viaddmin_u16x2(x, a, b);
+    if (OP == OP_VADDMNMX32) return __viaddmin_u32(x, a, b);
+    if (OP == OP_MIX_IADD_LOP) {
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(a));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x) : "r"(a), "r"(b));
+        return x;
+    }
+    if (OP == OP_MIX_VADDMNMX_IMAD) {
+        x = __viaddmin_u16x2(x, a, b);
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+        return x;
+    }
+    if (OP == OP_MIX_VADDMNMX_IADD) return __viaddmin_u16x2(x, a, b) + a + b;
+    if (OP == OP_MIX_VADDMNMX_LOP) {
+        x = __viaddmin_u16x2(x, a, b);
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x) : "r"(a), "r"(b));
+        return x;
+    }
+    if (OP == OP_ACS_CORE) {
+        uint32_t t = __viaddmin_u16x2(x, b, 0x00FF00FFu);
+        uint32_t n = __viaddmin_u16x2(a, b, t);
+        return n + 0x80008000u - t;
+    }
+    if (OP == OP_SHFL) return __shfl_xor_sync(0xffffffffu, x, 1);
+    if (OP == OP_BALLOT) return __ballot_sync(0xffffffffu, (int)x < 0) + a;
+    return x;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) bench(uint32_t* out, uint32_t seed_a, uint32_t seed_b, int iters,
+                                             long long* cycles) {
+    uint32_t x[CHAINS];
+    uint32_t a = seed_a + threadIdx.x, b = seed_b ^ (threadIdx.x * 2654435761u);
+    if (OP == OP_MNMX32 || OP == OP_VMNMX16 || OP == OP_VMNMX3_16) { a |= 0xFFF0FFF0u; b |= 0xFF00FF00u; }
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) x[c] = blockIdx.x * 977u + threadIdx.x * 31u + c * 0x01010101u;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int c = 0; c < CHAINS; c++) x[c] = step<OP>(x[c], a, b);
+        }
+    }
+    long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) acc ^= x[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(int nsm, int iters, uint32_t* d_out, long long* d_cyc, long long* h_cyc) {
+    const int blocks = nsm * 8, threads = 256;  // 8 x 256 = 2048 threads/SM = full occupancy
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    bench<OP><<<blocks, threads>>>(d_out, 3, 5, iters / 8 + 1, d_cyc);  // warm-up
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(e0));
+        bench<OP><<<blocks, threads>>>(d_out, 3, 5, iters, d_cyc);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaMemcpy(h_cyc, d_cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost));
+    double cyc = 0;
+    for (int i = 0; i < blocks; i++) cyc += (double)h_cyc[i];
+    cyc /= blocks;  // average cycles one block spent in the loop (8 blocks share an SM)
+    const double laneops = (double)blocks * threads * (double)iters * 8.0 * CHAINS * op_count[OP];
+    const double tops = laneops / (best * 1e-3) / 1e12;
+    // per-SM per-clock from the in-kernel cycle counter: 8 co-resident blocks run the whole time
+    const double per_sm_clk = (double)8 * threads * (double)iters * 8.0 * CHAINS * op_count[OP] / cyc;
+    printf("{\"op\": \"%s\", \"ms\": %.4f, \"tera_laneops_per_s\": %.3f, \"laneops_per_sm_per_clk\": %.1f, "
+           "\"eff_clock_mhz\": %.0f}\n",
+           op_name[OP], best, tops, per_sm_clk, tops * 1e12 / (per_sm_clk * nsm) / 1e6);
+    fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+    int iters = argc > 1 ? atoi(argv[1]) : 2000;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int nsm = prop.multiProcessorCount;
+    printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, nsm, prop.clockRate);
+    uint32_t* d_out;
+    long long *d_cyc, *h_cyc;
+    CK(cudaMalloc(&d_out, sizeof(uint32_t) * nsm * 8 * 256));
+    CK(cudaMalloc(&d_cyc, sizeof(long long) * nsm * 8));
+    h_cyc = (long long*)malloc(sizeof(long long) * nsm * 8);
+    run<OP_IADD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_LOP3>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_IMAD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_SHF>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_PRMT>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_MNMX32>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VIADD16>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VMNMX16>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VMNMX3_16>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VADDMNMX16>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VADDMNMX32>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_MIX_IADD_LOP>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_MIX_VADDMNMX_IMAD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_MIX_VADDMNMX_IADD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_MIX_VADDMNMX_LOP>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_ACS_CORE>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_SHFL>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_BALLOT>(nsm, iters, d_out, d_cyc, h_cyc);
+    return 0;
+}

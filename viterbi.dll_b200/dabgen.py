@@ -1,0 +1,217 @@
+"""Synthetic DAB/DAB+ traffic for parity tests and benchmarks.
+
+This is the portable counterpart of the generator inside the reference's only
+test driver (viterbi-benchmark/viterbi-benchmark.cpp): random bits -> K=7 rate-1/4
+convolutional encoder (polys 109,79,83,109; :64,304-311) -> 6 zero tail bits ->
+AWGN -> 8-bit soft symbols ``(int)(127.5 + 32*(+-amp + n))`` clipped to 0..255
+(:58-61,293-294,658-670).  MSVC rand() is not reproducible, so numpy / torch
+generators seeded by the caller are used instead.  The RS(120,110) side
+(systematic encoder, error injector, column interleaver) has no counterpart in the
+reference, which never tests RScheckSuperframe functionally.
+
+Nothing here is on the decode path; it only manufactures inputs.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+POLYS = (109, 79, 83, 109)  # viterbi-benchmark.cpp:64
+K = 7
+RATE = 4
+GAIN = 32.0
+OFFSET = 127.5
+
+
+def nsym(framebits: int) -> int:
+    """Soft symbols per frame: 4 per trellis step, F info + 6 tail steps."""
+    return RATE * (framebits + K - 1)
+
+
+def nout(framebits: int) -> int:
+    return (framebits + 7) // 8
+
+
+def noise_amp(ebn0_db: float) -> float:
+    """Signal amplitude in noise-sigma units (viterbi-benchmark.cpp:293-294)."""
+    esn0 = ebn0_db + 10.0 * math.log10(1.0 / RATE)
+    return 1.0 / math.sqrt(0.5 / 10.0 ** (esn0 / 10.0))
+
+
+def conv_encode(bits: np.ndarray) -> np.ndarray:
+    """bits [n, F] in {0,1} -> code bits [n, 4*(F+6)] (tail-terminated)."""
+    bits = np.asarray(bits, dtype=np.uint8)
+    n, f = bits.shape
+    padded = np.zeros((n, f + 2 * (K - 1)), dtype=np.uint8)  # 6 zeros before, 6 after
+    padded[:, K - 1 : K - 1 + f] = bits
+    steps = f + K - 1
+    out = np.empty((n, steps, RATE), dtype=np.uint8)
+    for j, poly in enumerate(POLYS):
+        acc = np.zeros((n, steps), dtype=np.uint8)
+        for d in range(K):  # bit d of the shift register = input d steps ago
+            if (poly >> d) & 1:
+                acc ^= padded[:, K - 1 - d : K - 1 - d + steps]
+        out[:, :, j] = acc
+    return out.reshape(n, steps * RATE)
+
+
+def soft_symbols(code_bits: np.ndarray, ebn0_db: float, rng: np.random.Generator) -> np.ndarray:
+    """AWGN channel + 8-bit quantiser of viterbi-benchmark.cpp:658-670."""
+    amp = noise_amp(ebn0_db)
+    x = rng.standard_normal(code_bits.shape, dtype=np.float32)
+    x += (code_bits.astype(np.float32) * 2.0 - 1.0) * np.float32(amp)
+    x = OFFSET + GAIN * x
+    return np.clip(np.trunc(x), 0, 255).astype(np.uint8)
+
+
+def pack_bits(bits: np.ndarray) -> np.ndarray:
+    """MSB-first packing, the layout deconvolve() writes (deconvolve.cpp:416-435)."""
+    return np.packbits(np.asarray(bits, dtype=np.uint8), axis=-1, bitorder="big")
+
+
+def make_frames(n: int, framebits: int, ebn0_db: float, seed: int):
+    """-> (symbols u8 [n, 4*(F+6)], packed info bits u8 [n, ceil(F/8)])."""
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, size=(n, framebits), dtype=np.uint8)
+    return soft_symbols(conv_encode(bits), ebn0_db, rng), pack_bits(bits)
+
+
+def lcg_symbols(seed: int, count: int) -> np.ndarray:
+    """LCG byte stream used by the known-answer vectors V3/V4."""
+    x = seed
+    out = np.empty(count, dtype=np.uint8)
+    for i in range(count):
+        x = (1103515245 * x + 12345) & 0x7FFFFFFF
+        out[i] = (x >> 16) & 0xFF
+    return out
+
+
+# ---------------------------------------------------------------------------
+# torch generators (device-side synthetic input for the large benchmark configs)
+# ---------------------------------------------------------------------------
+def make_frames_torch(n: int, framebits: int, ebn0_db: float, seed: int, device, chunk: int = 8192,
+                      want_bits: bool = False):
+    """Same channel model generated with torch on `device` -> u8 tensor [n, 4*(F+6)].
+
+    Used only to manufacture benchmark inputs already resident in HBM; returns
+    (symbols, packed_bits or None).
+    """
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    steps = framebits + K - 1
+    amp = noise_amp(ebn0_db)
+    syms = torch.empty((n, steps * RATE), dtype=torch.uint8, device=device)
+    packed = torch.empty((n, nout(framebits)), dtype=torch.uint8, device=device) if want_bits else None
+    weights = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=device)
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        bits = torch.randint(0, 2, (m, framebits), generator=g, device=device, dtype=torch.uint8)
+        padded = torch.zeros((m, framebits + 2 * (K - 1)), dtype=torch.uint8, device=device)
+        padded[:, K - 1 : K - 1 + framebits] = bits
+        code = torch.empty((m, steps, RATE), dtype=torch.uint8, device=device)
+        for j, poly in enumerate(POLYS):
+            acc = torch.zeros((m, steps), dtype=torch.uint8, device=device)
+            for d in range(K):
+                if (poly >> d) & 1:
+                    acc ^= padded[:, K - 1 - d : K - 1 - d + steps]
+            code[:, :, j] = acc
+        x = torch.randn((m, steps * RATE), generator=g, device=device, dtype=torch.float32)
+        x += (code.reshape(m, -1).to(torch.float32) * 2.0 - 1.0) * amp
+        x = OFFSET + GAIN * x
+        syms[lo : lo + m] = torch.clamp(torch.trunc(x), 0, 255).to(torch.uint8)
+        if want_bits:
+            if framebits % 8:
+                raise ValueError("want_bits needs framebits % 8 == 0")
+            packed[lo : lo + m] = (bits.reshape(m, -1, 8) * weights).sum(dim=2, dtype=torch.int32).to(torch.uint8)
+    return syms, packed
+
+
+# ---------------------------------------------------------------------------
+# Reed-Solomon RS(120,110) over GF(256)/0x11D, roots alpha^0..alpha^9
+# ---------------------------------------------------------------------------
+RS_N, RS_K, RS_T2 = 120, 110, 10
+
+
+def _gf_tables():
+    exp = np.zeros(512, dtype=np.int32)
+    log = np.zeros(256, dtype=np.int32)
+    sr = 1
+    for i in range(255):
+        exp[i] = sr
+        log[sr] = i
+        sr <<= 1
+        if sr & 0x100:
+            sr ^= 0x11D
+    exp[255:510] = exp[0:255]
+    return exp, log
+
+
+_EXP, _LOG = _gf_tables()
+
+
+def gf_mul(a, b):
+    a = np.asarray(a, dtype=np.int32)
+    b = np.asarray(b, dtype=np.int32)
+    r = _EXP[(_LOG[a] + _LOG[b]) % 255]
+    return np.where((a == 0) | (b == 0), 0, r).astype(np.uint8)
+
+
+def rs_generator_poly() -> np.ndarray:
+    """g(x) = prod_{i=0..9} (x - alpha^i), coefficients low -> high (11 entries)."""
+    g = np.array([1], dtype=np.uint8)
+    for i in range(RS_T2):
+        root = np.uint8(_EXP[i])
+        shifted = np.concatenate(([0], g)).astype(np.uint8)  # x * g
+        scaled = np.concatenate((gf_mul(g, root), [0])).astype(np.uint8)  # root * g
+        g = shifted ^ scaled
+    return g
+
+
+_GEN = rs_generator_poly()
+
+
+def rs_encode(msg: np.ndarray) -> np.ndarray:
+    """msg [n,110] -> systematic codewords [n,120]; byte 0 is the highest-degree coefficient."""
+    msg = np.asarray(msg, dtype=np.uint8)
+    n = msg.shape[0]
+    reg = np.zeros((n, RS_T2), dtype=np.uint8)  # reg[:, 0] = highest-degree remainder coefficient
+    ghi = _GEN[RS_T2 - 1 :: -1]  # g_9 .. g_0
+    for k in range(RS_K):
+        fb = msg[:, k] ^ reg[:, 0]
+        reg[:, :-1] = reg[:, 1:]
+        reg[:, -1] = 0
+        reg ^= gf_mul(fb[:, None], ghi[None, :])
+    return np.concatenate((msg, reg), axis=1)
+
+
+def rs_inject_errors(cw: np.ndarray, nerr: np.ndarray, rng: np.random.Generator) -> np.ndarray:
+    """XOR nerr[i] distinct non-zero byte errors into codeword i (cw [n,120])."""
+    cw = np.array(cw, dtype=np.uint8, copy=True)
+    n = cw.shape[0]
+    nerr = np.broadcast_to(np.asarray(nerr), (n,))
+    order = np.argsort(rng.random((n, RS_N)), axis=1)  # random distinct positions per row
+    vals = rng.integers(1, 256, size=(n, RS_N), dtype=np.uint8)
+    mask = np.arange(RS_N)[None, :] < nerr[:, None]
+    rows = np.repeat(np.arange(n), RS_N).reshape(n, RS_N)
+    cw[rows[mask], order[mask]] ^= vals[mask]
+    return cw
+
+
+def rs_interleave(cw: np.ndarray, s: int) -> np.ndarray:
+    """cw [n*s,120] -> superframes [n,120*s] with codeword j byte k at j + k*s (rschecksf.cpp:75-76)."""
+    n = cw.shape[0] // s
+    return np.ascontiguousarray(cw.reshape(n, s, RS_N).transpose(0, 2, 1)).reshape(n, RS_N * s)
+
+
+def make_superframes(n: int, s: int, seed: int, max_err: int = 7):
+    """-> (received [n,120*s], clean payload [n,110*s], errors per codeword [n,s])."""
+    rng = np.random.default_rng(seed)
+    msg = rng.integers(0, 256, size=(n * s, RS_K), dtype=np.uint8)
+    cw = rs_encode(msg)
+    nerr = rng.integers(0, max_err + 1, size=n * s)
+    rx = rs_inject_errors(cw, nerr, rng)
+    payload = np.ascontiguousarray(msg.reshape(n, s, RS_K).transpose(0, 2, 1)).reshape(n, RS_K * s)
+    return rs_interleave(rx, s), payload, nerr.reshape(n, s)
