@@ -1,0 +1,120 @@
+/* viterbi_b200.h -- C ABI of libviterbi_b200.so, a B200 (sm_100a) replacement for the FEC hot
+ * path of Drehrumbum/viterbi.dll.
+ *
+ * Two groups of entry points:
+ *   1. the reference's export surface (viterbi.def:4-8), same names, argument meaning and return
+ *      conventions, so a host that does LoadLibrary/GetProcAddress (viterbi-benchmark.cpp:201-229)
+ *      or dlopen/dlsym can switch libraries without code changes;
+ *   2. batched entry points (new): many DAB frames / DAB+ superframes per launch, with host-pointer
+ *      and device-pointer flavours.  This is the path that is measured.
+ *
+ * All functions are thread-safe.  There is no CPU fallback: every decode runs on the selected
+ * CUDA device, and failures are reported through the return value (see "save mode").
+ */
+#ifndef VITERBI_B200_H
+#define VITERBI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITERBI_B200_MAX_FRAMEBITS 9216u /* decision array bound of the reference, deconvolve.cpp:127 */
+
+/* ---------------------------------------------------------------------------------------------
+ * 1. Drop-in surface (viterbi.def:4-8)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces deconvolve(), deconvolve.cpp:551-554 (caller typedef viterbi-benchmark.cpp:72-73).
+ * Hard-output Viterbi decode of one K=7 rate-1/4 DAB frame.
+ *   framebits   info bits F (even, <= 9216); the frame carries F+6 trellis steps
+ *   piData      4*(F+6) words, one soft symbol per word; only the low byte is used
+ *               (deconvolve.cpp:219-228; README.md:19 out-of-range symbols)
+ *   inputLength ignored, as in the reference
+ *   output      ceil(F/8) bytes, MSB first
+ * Returns 0; returns 1 on bad arguments / device failure and from then on until initialize()
+ * ("save mode": exc_handler.cpp:204,214, viterbi_helpers.asm:183-186). */
+int deconvolve(unsigned int framebits, unsigned int* piData, int inputLength, unsigned char* output);
+
+/* Replaces RScheckSuperframe(), rschecksf.cpp:65-93 (caller typedef viterbi-benchmark.cpp:76-77).
+ * DAB+ superframe: RSDims column-interleaved RS(120,110) codewords, byte k of codeword j at
+ * p[j + k*RSDims].  Writes the 110 data bytes of each codeword to outVector with the same striding
+ * and returns the total number of corrected symbols; on the first uncorrectable codeword returns -1
+ * and leaves that column and all later ones untouched (rschecksf.cpp:80-88).  startIx is unused
+ * (rschecksf.cpp:69).  Returns -1 on device failure as well (exc_handler.cpp:116-124,208-211). */
+int RScheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsigned char* outVector);
+
+/* Same function under the spelling BASELINE.json uses. */
+int RSCheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsigned char* outVector);
+
+/* Replaces initialize(), dllmain.cpp:156-160: called on every receiver start.  Re-reads the
+ * configuration (here: environment VITERBI_B200_DEVICE), (re)creates the device context and
+ * clears save mode.  Returns non-zero (true) on success like the reference. */
+int initialize(void);
+
+/* Replaces GetCPUCaps(), viterbi_helpers.asm:48-157 / getcpucaps.h:27-38.  The CPU dispatcher is
+ * replaced by device selection: returns 0 (no CPU decoder variants exist in this library). */
+int GetCPUCaps(void);
+
+/* Replaces WakeUpYMM(), dllmain.cpp:54-56: no-op. */
+void WakeUpYMM(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2. Batched entry points (new)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Return codes of the batched API */
+#define FEC_OK 0
+#define FEC_ERR_ARG 1    /* NULL pointer, odd framebits, framebits > 9216, RSDims == 0 ... */
+#define FEC_ERR_DEVICE 2 /* CUDA failure; fec_last_error() has the text */
+
+/* n frames, one byte per soft symbol: syms [n][4*(F+6)], out [n][ceil(F/8)].  Host pointers
+ * (pageable or pinned; pinned memory from fec_host_alloc() makes the copies asynchronous). */
+int viterbi_deconvolve_batch(unsigned int framebits, const uint8_t* syms, size_t n, uint8_t* out);
+
+/* Same, QIRX layout: one uint32 per soft symbol, low byte used. */
+int viterbi_deconvolve_batch_u32(unsigned int framebits, const uint32_t* syms, size_t n, uint8_t* out);
+
+/* Device-pointer flavours: buffers already in HBM, work enqueued on `stream` (a cudaStream_t, NULL =
+ * default stream), no synchronisation.  d_syms must be 8-byte aligned. */
+int viterbi_deconvolve_batch_device(unsigned int framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
+                                    void* stream);
+int viterbi_deconvolve_batch_u32_device(unsigned int framebits, const uint32_t* d_syms, size_t n,
+                                        uint8_t* d_out, void* stream);
+
+/* n superframes with the same RSDims: in [n][120*RSDims], out [n][110*RSDims], ret [n].
+ * Per superframe identical to RScheckSuperframe(), including the partial-write rule: bytes of out
+ * belonging to the first failing column and later ones are not written. */
+int rs_check_superframe_batch(const uint8_t* in, unsigned int RSDims, size_t n, uint8_t* out, int32_t* ret);
+int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
+                                     int32_t* d_ret, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device selection and utilities (replace getcpucaps/setupdll per the design brief)
+ * ------------------------------------------------------------------------------------------- */
+int fec_device_count(void);
+int fec_set_device(int ordinal); /* selects the CUDA device used by the calling process */
+int fec_get_device(void);
+int fec_in_save_mode(void);
+const char* fec_last_error(void); /* thread-local text of the last failure, "" if none */
+
+/* pinned host memory for asynchronous staging */
+void* fec_host_alloc(size_t bytes);
+void fec_host_free(void* p);
+
+/* plain device memory helpers for hosts without their own CUDA runtime binding */
+void* fec_device_alloc(size_t bytes);
+void fec_device_free(void* p);
+int fec_memcpy_h2d(void* d_dst, const void* src, size_t bytes);
+int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
+int fec_device_synchronize(void);
+
+/* number of kernels this library has launched since load (for benchmark accounting) */
+unsigned long long fec_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITERBI_B200_H */

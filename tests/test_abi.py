@@ -1,0 +1,84 @@
+"""CPU tests of the drop-in boundary: libviterbi_b200.so loads without a GPU and exports every
+symbol include/viterbi_b200.h declares; without a device every entry point fails loudly (there is
+no CPU decode path in the product)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "viterbi_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"^[A-Za-z_][\w\s\*]*?\b(\w+)\s*\([^;{]*\)\s*;", text, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_reference_exports():
+    names = declared_functions()
+    # viterbi.def:4-8 plus the spelling used by BASELINE.json
+    for n in ("deconvolve", "initialize", "RScheckSuperframe", "RSCheckSuperframe", "GetCPUCaps", "WakeUpYMM"):
+        assert n in names
+    for n in ("viterbi_deconvolve_batch", "viterbi_deconvolve_batch_u32", "viterbi_deconvolve_batch_device",
+              "viterbi_deconvolve_batch_u32_device", "rs_check_superframe_batch", "rs_check_superframe_batch_device"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol(vb):
+    out = subprocess.run(["nm", "-D", "--defined-only", vb.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [n for n in declared_functions() if n not in exported]
+    assert not missing, missing
+    # nothing but the C ABI leaks out (built with -fvisibility=hidden)
+    extra = [n for n in exported if n not in declared_functions()]
+    assert not extra, extra
+
+
+def test_binding_covers_header(vb):
+    assert sorted(vb._SIGNATURES) == declared_functions()
+
+
+def test_library_does_not_link_the_oracle(vb):
+    out = subprocess.run(["ldd", vb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "viterbi_ref" not in out
+    for src in os.listdir(os.path.join(ROOT, "viterbi.dll_b200", "csrc")):
+        text = open(os.path.join(ROOT, "viterbi.dll_b200", "csrc", src)).read()
+        assert "oracle/" not in text and "fec_oracle" not in text, src
+
+
+def _no_gpu(vb):
+    return vb.lib.fec_device_count() == 0
+
+
+def test_fails_loudly_without_device(vb):
+    if not _no_gpu(vb):
+        pytest.skip("a CUDA device is present")
+    sym = np.full(4 * (64 + 6), 128, dtype=np.uint32)
+    rc, _ = vb.deconvolve(64, sym)
+    assert rc == 1 and vb.lib.fec_in_save_mode() == 1  # exc_handler.cpp:214 convention
+    assert b"CUDA" in vb.lib.fec_last_error() or b"cuda" in vb.lib.fec_last_error()
+    out = np.zeros(110, dtype=np.uint8)
+    assert vb.RScheckSuperframe(np.zeros(120, dtype=np.uint8), 0, 1, out) == -1
+    with pytest.raises(vb.FecError):
+        vb.deconvolve_batch(64, np.zeros((2, 280), dtype=np.uint8))
+    with pytest.raises(vb.FecError):
+        vb.rs_check_superframe_batch(np.zeros((2, 120), dtype=np.uint8), 1)
+    assert vb.initialize() is False  # no device to select
+    assert vb.lib.fec_in_save_mode() == 0  # initialize() clears the latch (dllmain.cpp:157)
+
+
+def test_argument_validation(vb):
+    z = np.zeros((1, 4 * 13), dtype=np.uint8)
+    assert vb.lib.viterbi_deconvolve_batch(7, z.ctypes.data_as(ctypes.c_void_p), 1, z.ctypes.data_as(ctypes.c_void_p)) == vb.FEC_ERR_ARG
+    assert vb.lib.viterbi_deconvolve_batch(9218, None, 1, None) == vb.FEC_ERR_ARG
+    assert vb.lib.viterbi_deconvolve_batch(768, None, 0, None) == vb.FEC_OK  # empty batch is a no-op
+    assert vb.lib.rs_check_superframe_batch(None, 0, 1, None, None) == vb.FEC_ERR_ARG
+    assert vb.lib.rs_check_superframe_batch(None, 4, 0, None, None) == vb.FEC_OK
+    assert vb.lib.GetCPUCaps() == 0
+    vb.lib.WakeUpYMM()

@@ -1,0 +1,114 @@
+"""GPU parity tests for the DAB+ superframe RS check: C ABI of libviterbi_b200.so against the
+CPU checker (compiled reference / C port) and the golden vectors.  Return values, corrected
+bytes and untouched bytes must all be identical."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from viterbi_dll_b200 import dabgen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device(vb):
+    assert vb.lib.fec_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    assert vb.initialize()
+
+
+def test_known_answers_through_dropin(vb, golden_dir):
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))
+    for e in kat["rs"]:
+        p = np.frombuffer(bytes.fromhex(e["in_hex"]), dtype=np.uint8)
+        out = np.full(110 * e["s"], e["out_prefill"], dtype=np.uint8)
+        assert vb.RScheckSuperframe(p, 0, e["s"], out) == e["ret"], e["name"]
+        assert out.tobytes().hex() == e["out_hex"], e["name"]
+        out2 = np.full(110 * e["s"], e["out_prefill"], dtype=np.uint8)
+        assert vb.lib.RSCheckSuperframe(p.ctypes.data, 0, e["s"], out2.ctypes.data) == e["ret"]
+        assert np.array_equal(out, out2)
+
+
+def test_golden_fixture_host_and_device(vb, golden_dir):
+    import torch
+
+    fx = np.load(os.path.join(golden_dir, "rs_fixture.npz"))
+    for s in (1, 2, 3, 4, 5, 6, 7, 8, 16, 24):
+        rx, want_out, want_ret = fx["s%d_in" % s], fx["s%d_out" % s], fx["s%d_ret" % s]
+        out, ret = vb.rs_check_superframe_batch(rx, s, fill=0xEE)
+        assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out), s
+        d_out = torch.full((rx.shape[0], 110 * s), 0xEE, dtype=torch.uint8, device="cuda")
+        d_out, d_ret = vb.rs_check_superframe_batch_device(torch.from_numpy(rx).cuda(), s, d_out)
+        assert np.array_equal(d_ret.cpu().numpy(), want_ret) and np.array_equal(d_out.cpu().numpy(), want_out), s
+
+
+@pytest.mark.parametrize("s", [1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 16, 24, 31, 64, 65, 127, 128, 129, 200])
+def test_random_superframes_match_checker(vb, checker, s):
+    n = 3000 if s <= 8 else 300 if s <= 32 else 40
+    rx, _, _ = dabgen.make_superframes(n, s, seed=40 + s)
+    want_out, want_ret = checker.rs_batch(rx, s, fill=0xEE)
+    out, ret = vb.rs_check_superframe_batch(rx, s, fill=0xEE)
+    assert np.array_equal(ret, want_ret), s
+    assert np.array_equal(out, want_out), s
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 127, 128, 129, 1001])
+def test_ragged_batch_sizes(vb, checker, n):
+    for s in (1, 5, 8):
+        rx, _, _ = dabgen.make_superframes(n, s, seed=n * 10 + s, max_err=6)
+        want_out, want_ret = checker.rs_batch(rx, s, fill=0x5A)
+        out, ret = vb.rs_check_superframe_batch(rx, s, fill=0x5A)
+        assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out), (n, s)
+
+
+def test_corrects_up_to_five_and_restores_payload(vb):
+    for s in (1, 8):
+        rx, payload, nerr = dabgen.make_superframes(2000, s, seed=9, max_err=5)
+        out, ret = vb.rs_check_superframe_batch(rx, s)
+        assert np.array_equal(out, payload)
+        assert np.array_equal(ret, nerr.sum(axis=1))
+
+
+def test_garbage_input_heavy_paths(vb, checker):
+    """Uniform random bytes: nearly every codeword is uncorrectable, lambda reaches degree 10,
+    occasional silent miscorrections (SURVEY KAT-R3b) must agree too."""
+    rng = np.random.default_rng(21)
+    for s in (1, 2):
+        rx = rng.integers(0, 256, size=(20000, 120 * s), dtype=np.uint8)
+        want_out, want_ret = checker.rs_batch(rx, s, fill=0xEE)
+        out, ret = vb.rs_check_superframe_batch(rx, s, fill=0xEE)
+        assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out)
+    # few-error patterns around the decoder limit incl. burst at the codeword ends
+    rx, _, _ = dabgen.make_superframes(20000, 1, seed=5, max_err=0)
+    rx[:, :6] ^= rng.integers(0, 256, size=(20000, 6), dtype=np.uint8)
+    rx[::2, 114:] ^= rng.integers(0, 256, size=(10000, 6), dtype=np.uint8)
+    want_out, want_ret = checker.rs_batch(rx, 1, fill=0xEE)
+    out, ret = vb.rs_check_superframe_batch(rx, 1, fill=0xEE)
+    assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out)
+
+
+def test_partial_write_rule_keeps_caller_bytes(vb, checker):
+    """Columns at and after the first failing one keep whatever the caller had in outVector."""
+    rng = np.random.default_rng(31)
+    s = 6
+    rx, _, _ = dabgen.make_superframes(500, s, seed=77, max_err=7)
+    prefill = rng.integers(0, 256, size=(500, 110 * s), dtype=np.uint8)
+    want = prefill.copy()
+    want_ret = np.zeros(500, np.int32)
+    for i in range(500):
+        want_ret[i] = checker.rs_check_superframe(rx[i], s, want[i])
+    out, ret = vb.rs_check_superframe_batch(rx, s, out=prefill.copy())
+    assert np.array_equal(ret, want_ret) and np.array_equal(out, want)
+    assert (want_ret == -1).any() and (want_ret >= 0).any()
+
+
+def test_one_million_superframes_bit_exact(vb, checker):
+    """BASELINE config 4: 10^6 superframes, s = 1..8, 0-7 byte errors per codeword."""
+    per_s = 125000 if checker.kind == "reference" else 8000
+    for s in range(1, 9):
+        rx, _, _ = dabgen.make_superframes(per_s, s, seed=900 + s)
+        want_out, want_ret = checker.rs_batch(rx, s, fill=0xEE)
+        out, ret = vb.rs_check_superframe_batch(rx, s, fill=0xEE)
+        assert np.array_equal(ret, want_ret), s
+        assert np.array_equal(out, want_out), s

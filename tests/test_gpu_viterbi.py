@@ -1,0 +1,151 @@
+"""GPU parity tests for the Viterbi path: libviterbi_b200.so (through its C ABI) against the
+CPU checker -- the reference compiled unmodified (oracle/_ref) when it was built, else the C
+port -- and against the golden vectors recorded from the reference.  Bit-exact or fail."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from viterbi_dll_b200 import dabgen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device(vb):
+    assert vb.lib.fec_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    assert vb.initialize()
+    yield
+    assert vb.lib.fec_in_save_mode() == 0
+
+
+def test_known_answers_through_dropin_deconvolve(vb, golden_dir):
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))
+    for e in kat["viterbi"]:
+        if e.get("symbols_hex"):
+            sym = np.frombuffer(bytes.fromhex(e["symbols_hex"]), dtype="<u4")
+        else:
+            sym = dabgen.lcg_symbols(e["lcg_seed"], 4 * (e["framebits"] + 6)).astype(np.uint32)
+        rc, out = vb.deconvolve(e["framebits"], sym)
+        assert rc == 0
+        assert hashlib.sha256(out.tobytes()).hexdigest() == e["out_sha256"], e["name"]
+
+
+def test_golden_fixture_host_and_device(vb, golden_dir):
+    import torch
+
+    fx = np.load(os.path.join(golden_dir, "viterbi_fixture.npz"))
+    for k in sorted(k[:-4] for k in fx.files if k.endswith("_sym")):
+        f = int(k.split("_F")[1])
+        sym, want = fx[k + "_sym"], fx[k + "_out"]
+        assert np.array_equal(vb.deconvolve_batch(f, sym), want), k
+        assert np.array_equal(vb.deconvolve_batch(f, sym.astype(np.uint32)), want), k + " (u32)"
+        d = torch.from_numpy(sym).cuda()
+        assert np.array_equal(vb.deconvolve_batch_device(f, d).cpu().numpy(), want), k + " (device)"
+        d32 = torch.from_numpy(sym.astype(np.int32)).cuda()
+        assert np.array_equal(vb.deconvolve_batch_device(f, d32).cpu().numpy(), want), k + " (device u32)"
+
+
+@pytest.mark.parametrize("framebits,ebn0,n", [(768, 3.0, 4096), (768, 0.0, 1000), (3072, 0.0, 700), (3072, 3.0, 1500),
+                                              (3072, 6.0, 700), (1536, 2.0, 513), (2304, 4.0, 257), (9216, 3.0, 130),
+                                              (2, 1.0, 200), (10, 1.0, 65), (100, 2.0, 63), (770, 3.0, 129), (772, 3.0, 64)])
+def test_random_frames_match_checker(vb, checker, framebits, ebn0, n):
+    sym, _ = dabgen.make_frames(n, framebits, ebn0, seed=framebits * 7 + n)
+    assert np.array_equal(vb.deconvolve_batch(framebits, sym), checker.deconvolve_batch(framebits, sym))
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 1000])
+def test_ragged_batch_sizes(vb, checker, n):
+    sym, _ = dabgen.make_frames(n, 768, 2.0, seed=n)
+    assert np.array_equal(vb.deconvolve_batch(768, sym), checker.deconvolve_batch(768, sym))
+
+
+def test_adversarial_symbols(vb, checker):
+    rng = np.random.default_rng(11)
+    for f in (768, 3072):
+        ns = 4 * (f + 6)
+        rows = [np.zeros(ns, np.uint8), np.full(ns, 128, np.uint8), np.full(ns, 255, np.uint8), np.full(ns, 127, np.uint8)]
+        rows += [rng.integers(0, 2, ns, dtype=np.uint8) * 255 for _ in range(60)]  # saturation / clamp heavy
+        rows += [rng.integers(0, 256, ns, dtype=np.uint8) for _ in range(60)]
+        rows += [rng.integers(120, 136, ns, dtype=np.uint8) for _ in range(30)]  # tie heavy
+        rows += [np.tile(np.array([0, 255, 255, 0], np.uint8), f + 6), np.tile(np.array([255, 0, 0, 255], np.uint8), f + 6)]
+        sym = np.stack(rows)
+        assert np.array_equal(vb.deconvolve_batch(f, sym), checker.deconvolve_batch(f, sym)), f
+
+
+def test_out_of_range_symbols_low_byte_only(vb, checker):
+    """README.md:19 edge case: words above 255 -- only the low byte counts (deconvolve.cpp:219-228)."""
+    rng = np.random.default_rng(12)
+    sym, _ = dabgen.make_frames(70, 768, 3.0, seed=5)
+    dirty = sym.astype(np.uint32) | (rng.integers(0, 1 << 24, size=sym.shape, dtype=np.uint32) << 8)
+    want = checker.deconvolve_batch(768, sym)
+    assert np.array_equal(vb.deconvolve_batch(768, dirty), want)
+    rc, out = vb.deconvolve(768, dirty[3])
+    assert rc == 0 and np.array_equal(out, want[3])
+
+
+def test_empty_and_zero_length(vb):
+    assert vb.deconvolve_batch(768, np.zeros((0, 3096), np.uint8)).shape == (0, 96)
+    assert vb.deconvolve_batch(0, np.zeros((5, 24), np.uint8)).shape == (5, 0)  # F = 0: nothing to write
+
+
+def test_ber_fer_curve_identical_to_checker(vb, checker):
+    """Eb/N0 sweep 0..6 dB (BASELINE config 3, reduced count): same decoded bits => same BER/FER."""
+    for eb in range(0, 7):
+        sym, bits = dabgen.make_frames(384, 3072, float(eb), seed=1000 + eb)
+        got, want = vb.deconvolve_batch(3072, sym), checker.deconvolve_batch(3072, sym)
+        assert np.array_equal(got, want), eb
+        err = np.unpackbits(got ^ bits, axis=1).sum(axis=1)
+        ber, fer = err.sum() / err.size / 3072, (err > 0).mean()
+        if eb == 0:
+            assert ber > 1e-2
+        if eb == 6:
+            assert ber < 1e-5 and fer < 0.02
+
+
+def test_full_size_fic_roundtrip_on_device(vb):
+    """BASELINE config 2 size (65,536 FIC blocks): encode -> noiseless channel -> decode == payload,
+    and mild noise is fully corrected.  Size-independent property, no CPU reference needed."""
+    import torch
+
+    n, f = 65536, 768
+    sym, bits = dabgen.make_frames_torch(n, f, 9.0, seed=3, device="cuda", want_bits=True)
+    out = vb.deconvolve_batch_device(f, sym)
+    torch.cuda.synchronize()
+    assert torch.equal(out, bits)
+
+
+def test_one_million_fic_frames_bit_exact(vb, checker):
+    """>= 10^6 random frames, bit-exact against the checker (north-star acceptance)."""
+    import torch
+
+    f, total, chunk = 768, 1 << 20, 1 << 17
+    if checker.kind != "reference":
+        total = 1 << 16  # the scalar port is slower; keep the CPU side bounded
+    bad = 0
+    for i in range(total // chunk if total >= chunk else 1):
+        m = min(chunk, total)
+        sym, _ = dabgen.make_frames_torch(m, f, 1.0 + (i % 5), seed=77 + i, device="cuda")
+        out = vb.deconvolve_batch_device(f, sym)
+        torch.cuda.synchronize()
+        want = checker.deconvolve_batch(f, sym.cpu().numpy())
+        bad += int((out.cpu().numpy() != want).any(axis=1).sum())
+    assert bad == 0
+
+
+def test_save_mode_latch(vb):
+    """exc_handler.cpp:204-214 convention: a fault makes deconvolve return 1 until initialize()."""
+    import ctypes
+
+    assert vb.lib.deconvolve(64, None, 0, None) == 1
+    assert vb.lib.fec_in_save_mode() == 1
+    rc, _ = vb.deconvolve(64, np.full(280, 128, np.uint32))
+    assert rc == 1
+    assert vb.initialize()
+    rc, out = vb.deconvolve(64, np.full(280, 128, np.uint32))
+    assert rc == 0 and out.tobytes().hex() == "fc0fc0fc0fc0fc3f"
+    # an unsupported frame length is rejected without latching
+    rc, _ = vb.deconvolve(7, np.zeros(52, np.uint32))
+    assert rc == 1 and vb.lib.fec_in_save_mode() == 0

@@ -1,0 +1,185 @@
+"""viterbi.dll_b200 -- host-side mirror of viterbi.dll's FEC interface over libviterbi_b200.so.
+
+The product is the C-ABI shared library built from ``csrc/`` (see include/viterbi_b200.h); this
+module is the thin ctypes binding the tests and the benchmark use.  Function names, argument
+meaning and return conventions follow the reference exports (viterbi.def:4-8):
+
+    deconvolve(framebits, piData, inputLength, output)          deconvolve.cpp:551-554
+    RScheckSuperframe(p, startIx, RSDims, outVector)            rschecksf.cpp:65-93
+    initialize()                                                dllmain.cpp:156-160
+
+plus the batched entry points.  There is NO CPU fallback: if the CUDA library cannot be built
+or loaded, importing this module raises.
+
+The directory name contains a dot, so it is imported through the loader shim
+``viterbi_dll_b200.py`` at the repository root (``import viterbi_dll_b200 as vb``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+from . import dabgen  # noqa: F401  (synthetic traffic generator, re-exported)
+
+_vp = ctypes.c_void_p
+MAX_FRAMEBITS = 9216
+FEC_OK, FEC_ERR_ARG, FEC_ERR_DEVICE = 0, 1, 2
+
+# every symbol include/viterbi_b200.h declares: (restype, argtypes)
+_SIGNATURES = {
+    "deconvolve": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_int, _vp]),
+    "RScheckSuperframe": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint, _vp]),
+    "RSCheckSuperframe": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint, _vp]),
+    "initialize": (ctypes.c_int, []),
+    "GetCPUCaps": (ctypes.c_int, []),
+    "WakeUpYMM": (None, []),
+    "viterbi_deconvolve_batch": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp]),
+    "viterbi_deconvolve_batch_u32": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp]),
+    "viterbi_deconvolve_batch_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
+    "viterbi_deconvolve_batch_u32_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
+    "rs_check_superframe_batch": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp]),
+    "rs_check_superframe_batch_device": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp, _vp]),
+    "fec_device_count": (ctypes.c_int, []),
+    "fec_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "fec_get_device": (ctypes.c_int, []),
+    "fec_in_save_mode": (ctypes.c_int, []),
+    "fec_last_error": (ctypes.c_char_p, []),
+    "fec_host_alloc": (_vp, [ctypes.c_size_t]),
+    "fec_host_free": (None, [_vp]),
+    "fec_device_alloc": (_vp, [ctypes.c_size_t]),
+    "fec_device_free": (None, [_vp]),
+    "fec_memcpy_h2d": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "fec_memcpy_d2h": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "fec_device_synchronize": (ctypes.c_int, []),
+    "fec_kernel_launches": (ctypes.c_ulonglong, []),
+}
+
+LIB_PATH = _build.LIB
+
+
+def _load() -> ctypes.CDLL:
+    path = _build.build_library()  # rebuilds only when sources are newer; raises without nvcc
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class FecError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != FEC_OK:
+        raise FecError("%s failed (rc=%d): %s" % (what, rc, (lib.fec_last_error() or b"").decode()))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+# -------------------------------------------------------------------------------------------
+# drop-in surface
+# -------------------------------------------------------------------------------------------
+def deconvolve(framebits: int, piData: np.ndarray, inputLength: int = 0, output: np.ndarray | None = None):
+    """One frame, QIRX layout (uint32 per soft symbol).  Returns (rc, output bytes)."""
+    sym = np.ascontiguousarray(piData, dtype=np.uint32)
+    if output is None:
+        output = np.zeros((framebits + 7) // 8, dtype=np.uint8)
+    rc = lib.deconvolve(framebits, _ptr(sym), inputLength, _ptr(output))
+    return rc, output
+
+
+def RScheckSuperframe(p: np.ndarray, startIx: int, RSDims: int, outVector: np.ndarray) -> int:
+    p = np.ascontiguousarray(p, dtype=np.uint8)
+    assert outVector.dtype == np.uint8 and outVector.flags.c_contiguous
+    return lib.RScheckSuperframe(_ptr(p), startIx, RSDims, _ptr(outVector))
+
+
+def initialize() -> bool:
+    return bool(lib.initialize())
+
+
+# -------------------------------------------------------------------------------------------
+# batched, host buffers
+# -------------------------------------------------------------------------------------------
+def deconvolve_batch(framebits: int, syms: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """syms [n, 4*(F+6)] uint8 (or uint32, QIRX layout) -> [n, ceil(F/8)] uint8."""
+    syms = np.ascontiguousarray(syms)
+    n = syms.shape[0]
+    if syms.shape[1] != 4 * (framebits + 6):
+        raise ValueError("syms must be [n, 4*(framebits+6)]")
+    if out is None:
+        out = np.zeros((n, (framebits + 7) // 8), dtype=np.uint8)
+    if syms.dtype == np.uint8:
+        rc = lib.viterbi_deconvolve_batch(framebits, _ptr(syms), n, _ptr(out))
+    elif syms.dtype == np.uint32:
+        rc = lib.viterbi_deconvolve_batch_u32(framebits, _ptr(syms), n, _ptr(out))
+    else:
+        raise TypeError("syms must be uint8 or uint32")
+    _check(rc, "viterbi_deconvolve_batch")
+    return out
+
+
+def rs_check_superframe_batch(rx: np.ndarray, RSDims: int, out: np.ndarray | None = None, fill: int = 0):
+    """rx [n, 120*s] -> (out [n, 110*s], ret [n] int32).  `out` is updated in place when given."""
+    rx = np.ascontiguousarray(rx, dtype=np.uint8)
+    n = rx.shape[0]
+    if out is None:
+        out = np.full((n, 110 * RSDims), fill, dtype=np.uint8)
+    ret = np.zeros(n, dtype=np.int32)
+    _check(lib.rs_check_superframe_batch(_ptr(rx), RSDims, n, _ptr(out), _ptr(ret)), "rs_check_superframe_batch")
+    return out, ret
+
+
+# -------------------------------------------------------------------------------------------
+# batched, device buffers (torch tensors are only used as handles to HBM and streams)
+# -------------------------------------------------------------------------------------------
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        import torch
+
+        return torch.cuda.current_stream().cuda_stream
+    return getattr(stream, "cuda_stream", stream)
+
+
+def deconvolve_batch_device(framebits: int, syms, out=None, stream=None):
+    """syms: CUDA uint8 tensor [n, 4*(F+6)] (or int32/uint32 words, QIRX layout).  Asynchronous on `stream`."""
+    import torch
+
+    n = syms.shape[0]
+    if out is None:
+        out = torch.empty((n, (framebits + 7) // 8), dtype=torch.uint8, device=syms.device)
+    assert syms.is_contiguous() and out.is_contiguous() and syms.shape[1] == 4 * (framebits + 6)
+    if syms.dtype == torch.uint8:
+        rc = lib.viterbi_deconvolve_batch_device(framebits, syms.data_ptr(), n, out.data_ptr(), _stream_ptr(stream))
+    else:
+        assert syms.element_size() == 4
+        rc = lib.viterbi_deconvolve_batch_u32_device(framebits, syms.data_ptr(), n, out.data_ptr(), _stream_ptr(stream))
+    _check(rc, "viterbi_deconvolve_batch_device")
+    return out
+
+
+def rs_check_superframe_batch_device(rx, RSDims: int, out, ret=None, stream=None):
+    """rx: CUDA uint8 tensor [n, 120*s]; out [n, 110*s] is updated in place (partial-write rule)."""
+    import torch
+
+    n = rx.shape[0]
+    if ret is None:
+        ret = torch.empty((n,), dtype=torch.int32, device=rx.device)
+    assert rx.is_contiguous() and out.is_contiguous() and ret.is_contiguous()
+    rc = lib.rs_check_superframe_batch_device(rx.data_ptr(), RSDims, n, out.data_ptr(), ret.data_ptr(), _stream_ptr(stream))
+    _check(rc, "rs_check_superframe_batch_device")
+    return out, ret
+
+
+def kernel_launches() -> int:
+    return int(lib.fec_kernel_launches())

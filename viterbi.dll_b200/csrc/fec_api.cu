@@ -1,0 +1,431 @@
+// fec_api.cu -- the C ABI of libviterbi_b200.so (include/viterbi_b200.h) over the CUDA runtime.
+//
+// Mirrors the reference's export surface (viterbi.def:4-8) and its failure convention
+// (exc_handler.cpp:204-214: after a fault deconvolve returns 1 and RScheckSuperframe -1 until
+// initialize() is called), and adds the batched entry points.  The CPU dispatcher / ini file
+// (setupdll.cpp) is replaced by device selection.  No CPU decode path exists here.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/viterbi_b200.h"
+#include "fec_internal.h"
+
+namespace fec {
+
+namespace {
+
+constexpr int kMaxDevices = 64;
+constexpr int kPipe = 3;  // host-path pipeline depth (streams / staging slots)
+
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_save_mode{0};
+std::atomic<int> g_device{-1};  // -1: use the calling thread's current device
+thread_local std::string t_error;
+
+struct DeviceState {
+    std::once_flag once;
+    cudaError_t init_status = cudaSuccess;
+    int num_sms = 0;
+};
+DeviceState g_dev[kMaxDevices];
+
+// One staging slot of the host-pointer pipeline: device input / output / scratch on its own stream.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    void* d_aux = nullptr;  // u32 staging (viterbi) or ret (rs)
+    void* d_scratch = nullptr;
+    void* h_pin = nullptr;  // pinned bounce buffer for the single-call drop-in path
+    size_t in_cap = 0, out_cap = 0, aux_cap = 0, scratch_cap = 0, pin_cap = 0;
+};
+
+struct HostPipe {
+    std::mutex mu;
+    int device = -1;
+    Slot slot[kPipe];
+};
+HostPipe g_pipe;
+
+bool fail(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return false;
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    t_error = buf;
+    (void)cudaGetLastError();  // clear the sticky-less error state
+    return true;
+}
+
+int bad_arg(const char* what) {
+    t_error = what;
+    return FEC_ERR_ARG;
+}
+
+// Resolve the device this call runs on and make sure its per-device state exists.
+DeviceState* device_state(int* ordinal_out = nullptr) {
+    int dev = g_device.load();
+    if (dev >= 0) {
+        if (fail(cudaSetDevice(dev), "cudaSetDevice")) return nullptr;
+    } else if (fail(cudaGetDevice(&dev), "cudaGetDevice")) {
+        return nullptr;
+    }
+    if (dev < 0 || dev >= kMaxDevices) {
+        t_error = "device ordinal out of range";
+        return nullptr;
+    }
+    DeviceState* st = &g_dev[dev];
+    std::call_once(st->once, [st, dev] {
+        cudaDeviceProp prop;
+        st->init_status = cudaGetDeviceProperties(&prop, dev);
+        if (st->init_status != cudaSuccess) return;
+        st->num_sms = prop.multiProcessorCount;
+        st->init_status = rs_upload_tables();
+        if (st->init_status != cudaSuccess) return;
+        // keep stream-ordered scratch allocations cached in the pool between calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    });
+    if (fail(st->init_status, "device init")) return nullptr;
+    if (ordinal_out) *ordinal_out = dev;
+    return st;
+}
+
+bool grow(void** p, size_t* cap, size_t need, bool pinned = false) {
+    if (need <= *cap) return true;
+    if (*p) {
+        if (pinned)
+            cudaFreeHost(*p);
+        else
+            cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+    }
+    const size_t want = need + need / 4;
+    cudaError_t e = pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+    if (fail(e, pinned ? "cudaMallocHost" : "cudaMalloc")) return false;
+    *cap = want;
+    return true;
+}
+
+void release_pipe() {
+    for (Slot& s : g_pipe.slot) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_aux) cudaFree(s.d_aux);
+        if (s.d_scratch) cudaFree(s.d_scratch);
+        if (s.h_pin) cudaFreeHost(s.h_pin);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = Slot();
+    }
+    g_pipe.device = -1;
+}
+
+// g_pipe.mu must be held
+bool prepare_pipe(int dev) {
+    if (g_pipe.device != dev) {
+        if (g_pipe.device >= 0) {
+            cudaSetDevice(g_pipe.device);
+            release_pipe();
+            cudaSetDevice(dev);
+        }
+        g_pipe.device = dev;
+    }
+    for (Slot& s : g_pipe.slot)
+        if (!s.stream && fail(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    return true;
+}
+
+bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= VITERBI_B200_MAX_FRAMEBITS; }
+
+// Enqueue one batch that is already in device memory.  Scratch is stream-ordered.
+int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
+               cudaStream_t stream, void* scratch, size_t scratch_cap) {
+    if (n == 0 || framebits == 0) return FEC_OK;
+    const int blocks = viterbi_grid_blocks(st->num_sms, n);
+    const size_t need = viterbi_scratch_bytes(blocks, framebits);
+    void* ws = scratch;
+    const bool own = (ws == nullptr) || scratch_cap < need;
+    if (own && fail(cudaMallocAsync(&ws, need, stream), "cudaMallocAsync(scratch)")) return FEC_ERR_DEVICE;
+    cudaError_t e = launch_viterbi_pair(d_syms, d_out, ws, n, framebits, blocks, stream);
+    if (own) (void)cudaFreeAsync(ws, stream);
+    return fail(e, "viterbi kernel launch") ? FEC_ERR_DEVICE : FEC_OK;
+}
+
+// Host-pointer batch: chunks pipelined over kPipe streams (H2D | kernel | D2H overlap).
+int vit_host(unsigned framebits, const void* syms, bool is_u32, size_t n, uint8_t* out) {
+    if (!vit_args_ok(framebits)) return bad_arg("framebits must be even and <= 9216");
+    if (n == 0 || framebits == 0) return FEC_OK;
+    if (!syms || !out) return bad_arg("null pointer");
+    int dev;
+    DeviceState* st = device_state(&dev);
+    if (!st) return FEC_ERR_DEVICE;
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
+
+    const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
+    const size_t in_row = nsym * (is_u32 ? 4 : 1);
+    // chunk: about 64 MiB of u8 symbols, at least one full wave of the kernel grid
+    size_t chunk = (64u << 20) / nsym;
+    const size_t wave = (size_t)st->num_sms * kVitMinBlocks * (kVitThreads / 32) * 64;
+    if (chunk < wave) chunk = wave;
+    if (chunk > n) chunk = n;
+    int rc = FEC_OK;
+    size_t done = 0;
+    for (int k = 0; done < n && rc == FEC_OK; k++) {
+        Slot& s = g_pipe.slot[k % kPipe];
+        const size_t m = (n - done < chunk) ? n - done : chunk;
+        // the slot's previous chunk must have left its buffers
+        if (fail(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize")) { rc = FEC_ERR_DEVICE; break; }
+        const int blocks = viterbi_grid_blocks(st->num_sms, m);
+        if (!grow(&s.d_in, &s.in_cap, m * nsym) || !grow(&s.d_out, &s.out_cap, m * nout) ||
+            !grow(&s.d_scratch, &s.scratch_cap, viterbi_scratch_bytes(blocks, framebits)) ||
+            (is_u32 && !grow(&s.d_aux, &s.aux_cap, m * in_row))) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        const uint8_t* src = (const uint8_t*)syms + done * in_row;
+        if (is_u32) {
+            if (fail(cudaMemcpyAsync(s.d_aux, src, m * in_row, cudaMemcpyHostToDevice, s.stream), "H2D") ||
+                fail(launch_compact_symbols((const uint32_t*)s.d_aux, (uint8_t*)s.d_in, m * nsym, st->num_sms, s.stream),
+                     "compact kernel")) {
+                rc = FEC_ERR_DEVICE;
+                break;
+            }
+        } else if (fail(cudaMemcpyAsync(s.d_in, src, m * nsym, cudaMemcpyHostToDevice, s.stream), "H2D")) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        rc = vit_device(st, framebits, (const uint8_t*)s.d_in, m, (uint8_t*)s.d_out, s.stream, s.d_scratch, s.scratch_cap);
+        if (rc != FEC_OK) break;
+        if (fail(cudaMemcpyAsync(out + done * nout, s.d_out, m * nout, cudaMemcpyDeviceToHost, s.stream), "D2H")) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        done += m;
+    }
+    for (Slot& s : g_pipe.slot)
+        if (s.stream && fail(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
+    return rc;
+}
+
+int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret) {
+    if (s == 0 || s > 1024) return bad_arg("RSDims must be 1..1024");
+    if (n == 0) return FEC_OK;
+    if (!in || !out || !ret) return bad_arg("null pointer");
+    int dev;
+    DeviceState* st = device_state(&dev);
+    if (!st) return FEC_ERR_DEVICE;
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
+    const size_t in_row = 120 * (size_t)s, out_row = 110 * (size_t)s;
+    size_t chunk = (32u << 20) / in_row;
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    int rc = FEC_OK;
+    size_t done = 0;
+    for (int k = 0; done < n && rc == FEC_OK; k++) {
+        Slot& sl = g_pipe.slot[k % kPipe];
+        const size_t m = (n - done < chunk) ? n - done : chunk;
+        if (fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize")) { rc = FEC_ERR_DEVICE; break; }
+        if (!grow(&sl.d_in, &sl.in_cap, m * in_row) || !grow(&sl.d_out, &sl.out_cap, m * out_row) ||
+            !grow(&sl.d_aux, &sl.aux_cap, m * sizeof(int32_t))) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        // the partial-write rule needs the caller's current output bytes on the device
+        if (fail(cudaMemcpyAsync(sl.d_in, in + done * in_row, m * in_row, cudaMemcpyHostToDevice, sl.stream), "H2D") ||
+            fail(cudaMemcpyAsync(sl.d_out, out + done * out_row, m * out_row, cudaMemcpyHostToDevice, sl.stream), "H2D out") ||
+            fail(launch_rs_superframes((const uint8_t*)sl.d_in, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux, m, s, st->num_sms,
+                                       sl.stream),
+                 "rs kernel launch") ||
+            fail(cudaMemcpyAsync(out + done * out_row, sl.d_out, m * out_row, cudaMemcpyDeviceToHost, sl.stream), "D2H") ||
+            fail(cudaMemcpyAsync(ret + done, sl.d_aux, m * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ret")) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        done += m;
+    }
+    for (Slot& sl : g_pipe.slot)
+        if (sl.stream && fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
+    return rc;
+}
+
+}  // namespace
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+}  // namespace fec
+
+using namespace fec;
+
+// the library is built with -fvisibility=hidden; only the C ABI below is exported
+#pragma GCC visibility push(default)
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// drop-in surface
+// ---------------------------------------------------------------------------------------------
+int deconvolve(unsigned int framebits, unsigned int* piData, int inputLength, unsigned char* output) {
+    (void)inputLength;
+    if (g_save_mode.load()) return 1;  // decon_savemode, viterbi_helpers.asm:183-186
+    const int rc = vit_host(framebits, piData, true, 1, output);
+    if (rc == FEC_OK) return 0;
+    // The reference latches save mode after a fault inside the decoder (NULL buffers give an
+    // access violation there, viterbi-benchmark.cpp:457-464); a device failure is our equivalent.
+    // An unsupported framebits value never faults in the reference, so it does not latch.
+    if (rc == FEC_ERR_DEVICE || !piData || !output) g_save_mode.store(1);  // exc_handler.cpp:214
+    return 1;
+}
+
+int RScheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsigned char* outVector) {
+    (void)startIx;
+    if (RSDims == 0) return 0;  // the reference's column loop does not execute
+    int32_t ret = -1;
+    const int rc = rs_host(p, RSDims, 1, outVector, &ret);
+    if (rc != FEC_OK) return -1;  // exc_handler.cpp:208-211
+    return ret;
+}
+
+int RSCheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsigned char* outVector) {
+    return RScheckSuperframe(p, startIx, RSDims, outVector);
+}
+
+int initialize(void) {
+    g_save_mode.store(0);  // dllmain.cpp:157
+    t_error.clear();
+    const char* env = getenv("VITERBI_B200_DEVICE");
+    if (env && *env) g_device.store(atoi(env));
+    return device_state() != nullptr;
+}
+
+int GetCPUCaps(void) { return 0; }
+
+void WakeUpYMM(void) {}
+
+// ---------------------------------------------------------------------------------------------
+// batched API
+// ---------------------------------------------------------------------------------------------
+int viterbi_deconvolve_batch(unsigned int framebits, const uint8_t* syms, size_t n, uint8_t* out) {
+    return vit_host(framebits, syms, false, n, out);
+}
+
+int viterbi_deconvolve_batch_u32(unsigned int framebits, const uint32_t* syms, size_t n, uint8_t* out) {
+    return vit_host(framebits, syms, true, n, out);
+}
+
+int viterbi_deconvolve_batch_device(unsigned int framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
+                                    void* stream) {
+    if (!vit_args_ok(framebits)) return bad_arg("framebits must be even and <= 9216");
+    if (n == 0 || framebits == 0) return FEC_OK;
+    if (!d_syms || !d_out) return bad_arg("null pointer");
+    if (reinterpret_cast<uintptr_t>(d_syms) & 7) return bad_arg("d_syms must be 8-byte aligned");
+    DeviceState* st = device_state();
+    if (!st) return FEC_ERR_DEVICE;
+    return vit_device(st, framebits, d_syms, n, d_out, (cudaStream_t)stream, nullptr, 0);
+}
+
+int viterbi_deconvolve_batch_u32_device(unsigned int framebits, const uint32_t* d_syms, size_t n, uint8_t* d_out,
+                                        void* stream) {
+    if (!vit_args_ok(framebits)) return bad_arg("framebits must be even and <= 9216");
+    if (n == 0 || framebits == 0) return FEC_OK;
+    if (!d_syms || !d_out) return bad_arg("null pointer");
+    if (reinterpret_cast<uintptr_t>(d_syms) & 15) return bad_arg("d_syms must be 16-byte aligned");
+    DeviceState* st = device_state();
+    if (!st) return FEC_ERR_DEVICE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nsym = 4 * ((size_t)framebits + 6) * n;
+    void* d_u8 = nullptr;
+    if (fail(cudaMallocAsync(&d_u8, nsym, s), "cudaMallocAsync(u8 symbols)")) return FEC_ERR_DEVICE;
+    int rc = fail(launch_compact_symbols(d_syms, (uint8_t*)d_u8, nsym, st->num_sms, s), "compact kernel") ? FEC_ERR_DEVICE
+                                                                                                          : FEC_OK;
+    if (rc == FEC_OK) rc = vit_device(st, framebits, (const uint8_t*)d_u8, n, d_out, s, nullptr, 0);
+    (void)cudaFreeAsync(d_u8, s);
+    return rc;
+}
+
+int rs_check_superframe_batch(const uint8_t* in, unsigned int RSDims, size_t n, uint8_t* out, int32_t* ret) {
+    return rs_host(in, RSDims, n, out, ret);
+}
+
+int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
+                                     int32_t* d_ret, void* stream) {
+    if (RSDims == 0 || RSDims > 1024) return bad_arg("RSDims must be 1..1024");
+    if (n == 0) return FEC_OK;
+    if (!d_in || !d_out || !d_ret) return bad_arg("null pointer");
+    DeviceState* st = device_state();
+    if (!st) return FEC_ERR_DEVICE;
+    return fail(launch_rs_superframes(d_in, d_out, d_ret, n, RSDims, st->num_sms, (cudaStream_t)stream), "rs kernel launch")
+               ? FEC_ERR_DEVICE
+               : FEC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device selection and utilities
+// ---------------------------------------------------------------------------------------------
+int fec_device_count(void) {
+    int n = 0;
+    if (fail(cudaGetDeviceCount(&n), "cudaGetDeviceCount")) return 0;
+    return n;
+}
+
+int fec_set_device(int ordinal) {
+    if (ordinal < 0 || ordinal >= kMaxDevices) return bad_arg("device ordinal out of range");
+    if (fail(cudaSetDevice(ordinal), "cudaSetDevice")) return FEC_ERR_DEVICE;
+    g_device.store(ordinal);
+    return device_state() ? FEC_OK : FEC_ERR_DEVICE;
+}
+
+int fec_get_device(void) {
+    int dev = g_device.load();
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return -1;
+    return dev;
+}
+
+int fec_in_save_mode(void) { return g_save_mode.load(); }
+
+const char* fec_last_error(void) { return t_error.c_str(); }
+
+void* fec_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (fail(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost")) return nullptr;
+    return p;
+}
+
+void fec_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+void* fec_device_alloc(size_t bytes) {
+    if (!device_state()) return nullptr;
+    void* p = nullptr;
+    if (fail(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) return nullptr;
+    return p;
+}
+
+void fec_device_free(void* p) {
+    if (p) cudaFree(p);
+}
+
+int fec_memcpy_h2d(void* d_dst, const void* src, size_t bytes) {
+    return fail(cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D") ? FEC_ERR_DEVICE : FEC_OK;
+}
+
+int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes) {
+    return fail(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy D2H") ? FEC_ERR_DEVICE : FEC_OK;
+}
+
+int fec_device_synchronize(void) { return fail(cudaDeviceSynchronize(), "cudaDeviceSynchronize") ? FEC_ERR_DEVICE : FEC_OK; }
+
+unsigned long long fec_kernel_launches(void) { return g_launches.load(); }
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,32 @@
+// fec_internal.h -- declarations shared by the kernels and the C-ABI layer (not installed).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace fec {
+
+// Viterbi throughput kernel launch shape: 128 threads (4 warps, one per SM sub-partition) and
+// up to kVitMinBlocks resident blocks per SM.
+constexpr int kVitThreads = 128;
+constexpr int kVitMinBlocks = 3;
+
+constexpr int kRsThreads = 128;
+
+void count_launch();
+
+size_t viterbi_scratch_bytes(int grid_blocks, uint32_t framebits);
+int viterbi_grid_blocks(int num_sms, unsigned long long nframes);
+cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_scratch, unsigned long long nframes,
+                                uint32_t framebits, int grid_blocks, cudaStream_t stream);
+cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t nsymbols, int num_sms,
+                                   cudaStream_t stream);
+
+size_t rs_smem_bytes(uint32_t s, uint32_t sf_per_block);
+uint32_t rs_superframes_per_block(uint32_t s);
+cudaError_t rs_upload_tables();
+cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, unsigned long long nsf,
+                                  uint32_t s, int num_sms, cudaStream_t stream);
+
+}  // namespace fec

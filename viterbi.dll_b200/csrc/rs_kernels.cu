@@ -1,0 +1,336 @@
+// rs_kernels.cu -- sm_100a kernel for the DAB+ superframe Reed-Solomon check.
+//
+// Replaces RScheckSuperframe / DECODE_RS (rschecksf.cpp:65-93, 199-377) for batches of
+// superframes: RS(120,110) = RS(255,245) shortened by 135, GF(256) poly 0x11D, roots a^0..a^9,
+// errors-only Berlekamp-Massey / Chien / Forney, including the reference's quirks (roots inside
+// the virtual padding are counted but not applied, unreduced Forney exponent, no den==0 test,
+// "first failing column aborts the superframe" partial-write rule).
+//
+// Layout: a block stages a tile of whole superframes in shared memory with coalesced 16-byte
+// loads (this is also the column de-interleave: codeword j byte k sits at tile[k*s + j]), one
+// thread decodes one codeword in place, a shared-memory atomicMin finds the first failing
+// column of each superframe, and the 110*s data bytes are written back coalesced, masked by
+// that column.
+//
+// The syndrome stage differs from the reference's 10 Horner chains (1190 table steps per
+// codeword): the codeword is reduced modulo the generator polynomial with a byte-wide LFSR
+// (one 16-byte table row per data byte).  The remainder is zero iff all ten syndromes are zero,
+// so clean codewords stop there; otherwise S_i = rem(a^i) (100 table steps).  The syndromes are
+// the same field elements either way, so every later stage sees the reference's values.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "fec_internal.h"
+
+namespace fec {
+
+namespace {
+
+constexpr int NN = 255, NROOTS = 10, PAD = 135, CW = 120, DATA = 110;
+
+struct RsTables {
+    uint8_t ato[768];   // alpha^(i mod 255), dllmain.cpp:145-146
+    uint8_t iof[256];   // log, log(0) = 255, dllmain.cpp:131-143
+    uint4 lfsr[256];    // c * (g(x) - x^10): coefficients x^0..x^9 in bytes 0..9
+};
+
+__constant__ RsTables c_tables;
+
+// rschecksf.cpp:50-52
+__device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u) >> 24; }
+
+// Decode one codeword stored at col[k * stride], k = 0..119, in place.  Returns the number of
+// roots found (= corrected symbols as the reference counts them), 0 for a clean word, -1 if
+// uncorrectable.
+__device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __restrict__ ato,
+                                const uint8_t* __restrict__ iof, const uint4* __restrict__ lfsr) {
+    // ---- remainder of cw(x) mod g(x); cw[0] is the highest-degree coefficient -----------------
+    uint32_t r0 = 0, r1 = 0, r2 = 0;  // coefficients x^0..x^3 | x^4..x^7 | x^8,x^9
+#pragma unroll 4
+    for (int k = 0; k < CW; k++) {
+        const uint32_t c = r2 >> 8;  // coefficient of x^9 moves to x^10 and is reduced away
+        const uint4 row = lfsr[c];
+        r2 = ((r2 << 8) & 0xFF00u) | (r1 >> 24);
+        r1 = (r1 << 8) | (r0 >> 24);
+        r0 = (r0 << 8) | col[(size_t)k * stride];
+        r0 ^= row.x;
+        r1 ^= row.y;
+        r2 ^= row.z;
+    }
+    if ((r0 | r1 | r2) == 0u) return 0;  // all syndromes zero (rschecksf.cpp:224-230)
+
+    // ---- syndromes S_i = rem(alpha^i), then index form (rschecksf.cpp:232-233) ------------------
+    uint8_t syn[NROOTS];
+    {
+        uint32_t lg[NROOTS];
+#pragma unroll
+        for (int k = 0; k < NROOTS; k++) {
+            const uint32_t v = ((k < 4 ? r0 : k < 8 ? r1 : r2) >> (8 * (k & 3))) & 0xFFu;
+            lg[k] = iof[v];
+        }
+#pragma unroll
+        for (int i = 0; i < NROOTS; i++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < NROOTS; k++)
+                if (lg[k] != NN) acc ^= ato[lg[k] + i * k];  // <= 254 + 81
+            syn[i] = iof[acc];
+        }
+    }
+
+    // ---- Berlekamp-Massey (rschecksf.cpp:236-284): lambda polynomial form, b / syn index form ---
+    uint8_t lam[NROOTS + 1], b[NROOTS + 1], nxt[NROOTS + 1];
+#pragma unroll
+    for (int i = 0; i <= NROOTS; i++) {
+        lam[i] = (i == 0) ? 1 : 0;
+        b[i] = (i == 0) ? 0 : NN;
+    }
+    int el = 0;
+#pragma unroll
+    for (int r = 1; r <= NROOTS; r++) {
+        uint32_t discr = 0;
+#pragma unroll
+        for (int i = 0; i < r; i++)
+            if (lam[i] != 0 && syn[r - i - 1] != NN) discr ^= ato[iof[lam[i]] + syn[r - i - 1]];
+        discr = iof[discr];
+        if (discr == NN) {
+#pragma unroll
+            for (int i = NROOTS; i > 0; i--) b[i] = b[i - 1];
+            b[0] = NN;
+        } else {
+            nxt[0] = lam[0];
+#pragma unroll
+            for (int i = 0; i < NROOTS; i++) {
+                nxt[i + 1] = lam[i + 1];
+                if (b[i] != NN) nxt[i + 1] ^= ato[discr + b[i]];
+            }
+            if (2 * el <= r - 1) {
+                el = r - el;
+#pragma unroll
+                for (int i = 0; i <= NROOTS; i++)
+                    b[i] = (lam[i] == 0) ? (uint8_t)NN : (uint8_t)mod255(iof[lam[i]] - discr + NN);
+            } else {
+#pragma unroll
+                for (int i = NROOTS; i > 0; i--) b[i] = b[i - 1];
+                b[0] = NN;
+            }
+#pragma unroll
+            for (int i = 0; i <= NROOTS; i++) lam[i] = nxt[i];
+        }
+    }
+
+    int deg_lambda = 0;
+#pragma unroll
+    for (int i = 0; i <= NROOTS; i++) {
+        lam[i] = iof[lam[i]];
+        if (lam[i] != NN) deg_lambda = i;
+    }
+
+    // ---- Chien search (rschecksf.cpp:296-320) ---------------------------------------------------
+    uint32_t e[NROOTS + 1];
+#pragma unroll
+    for (int j = 1; j <= NROOTS; j++) e[j] = lam[j];
+    uint8_t root[NROOTS + 1];
+    int count = 0;
+    for (int i = 1; i <= NN; i++) {
+        uint32_t q = 1;
+#pragma unroll
+        for (int j = NROOTS; j > 0; j--)
+            if (j <= deg_lambda && e[j] != NN) {
+                e[j] = mod255(e[j] + j);
+                q ^= ato[e[j]];
+            }
+        if (q != 0) continue;
+#pragma unroll
+        for (int c = 0; c < NROOTS; c++)
+            if (c == count) root[c] = (uint8_t)i;
+        if (++count == deg_lambda) break;
+    }
+    if (deg_lambda != count) return -1;  // rschecksf.cpp:325-326
+
+    // ---- omega(x) = syn(x) lambda(x) mod x^10, index form (rschecksf.cpp:331-341) ----------------
+    const int deg_omega = deg_lambda - 1;
+    uint8_t om[NROOTS];
+#pragma unroll
+    for (int i = 0; i < NROOTS; i++) {
+        uint32_t tmp = 0;
+#pragma unroll
+        for (int j = 0; j <= i; j++)
+            if (syn[i - j] != NN && lam[j] != NN) tmp ^= ato[syn[i - j] + lam[j]];
+        om[i] = (i <= deg_omega) ? iof[tmp] : (uint8_t)NN;
+    }
+
+    // ---- Forney (rschecksf.cpp:346-374) ---------------------------------------------------------
+#pragma unroll
+    for (int c = NROOTS - 1; c >= 0; c--) {
+        if (c >= count) continue;
+        const uint32_t rj = root[c];
+        if (rj < PAD + 1) continue;  // root in the virtual padding: counted, not applied
+        uint32_t num1 = 0;
+#pragma unroll
+        for (int i = NROOTS - 1; i >= 0; i--)
+            if (i <= deg_omega && om[i] != NN) num1 ^= ato[mod255(om[i] + (uint32_t)i * rj)];
+        if (!num1) continue;
+        const uint32_t num2 = ato[NN - rj];
+        uint32_t den = 0;
+        const int top = (deg_lambda < NROOTS - 1 ? deg_lambda : NROOTS - 1) & ~1;
+#pragma unroll
+        for (int i = 8; i >= 0; i -= 2)
+            if (i <= top && lam[i + 1] != NN) den ^= ato[mod255(lam[i + 1] + (uint32_t)i * rj)];
+        // exponent used unreduced: the table has 768 entries (viterbi.h:101, rschecksf.cpp:366-370)
+        col[(size_t)(rj - 1 - PAD) * stride] ^= ato[iof[num1] + iof[num2] + (NN - iof[den])];
+    }
+    return count;
+}
+
+}  // namespace
+
+// One block = `sf_per_block` whole superframes; dynamic shared memory:
+//   [tables: ato 768 | iof 256 | lfsr 4096] [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
+__global__ void __launch_bounds__(kRsThreads)
+rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
+                     unsigned long long nsf, uint32_t s, uint32_t sf_per_block) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint4* s_lfsr = reinterpret_cast<uint4*>(smem);
+    uint8_t* s_ato = smem + 4096;
+    uint8_t* s_iof = s_ato + 768;
+    int* s_fail = reinterpret_cast<int*>(s_iof + 256);
+    int* s_sum = s_fail + sf_per_block;
+    uint8_t* tile = reinterpret_cast<uint8_t*>(s_sum + sf_per_block);
+    tile += (16 - (reinterpret_cast<uintptr_t>(tile) & 15)) & 15;
+
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < 256; i += blockDim.x) s_lfsr[i] = c_tables.lfsr[i];
+    for (uint32_t i = tid; i < 768; i += blockDim.x) s_ato[i] = c_tables.ato[i];
+    for (uint32_t i = tid; i < 256; i += blockDim.x) s_iof[i] = c_tables.iof[i];
+
+    const size_t sf_in = (size_t)CW * s, sf_out = (size_t)DATA * s;
+    const unsigned long long nblk = (nsf + sf_per_block - 1) / sf_per_block;
+    for (unsigned long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const unsigned long long sf0 = blk * sf_per_block;
+        const uint32_t nloc = (uint32_t)((nsf - sf0 < sf_per_block) ? (nsf - sf0) : sf_per_block);
+        const size_t bytes = sf_in * nloc;
+        const uint8_t* src = in + sf0 * sf_in;
+        __syncthreads();  // previous tile fully written out / tables loaded
+        // ---- stage the tile: coalesced 8-byte loads (120*s*sf0 is always a multiple of 8) ----------
+        if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+            const size_t nvec = bytes / 8;  // bytes is a multiple of 8 as well
+            for (size_t i = tid; i < nvec; i += blockDim.x)
+                reinterpret_cast<uint2*>(tile)[i] = __ldg(reinterpret_cast<const uint2*>(src) + i);
+        } else {
+            for (size_t i = tid; i < bytes; i += blockDim.x) tile[i] = __ldg(src + i);
+        }
+        for (uint32_t i = tid; i < nloc; i += blockDim.x) {
+            s_fail[i] = (int)s;  // "no column failed"
+            s_sum[i] = 0;
+        }
+        __syncthreads();
+        // ---- decode: one thread per codeword, corrections applied in place in the tile ------------
+        const uint32_t ncw = nloc * s;
+        for (uint32_t c = tid; c < ncw; c += blockDim.x) {
+            const uint32_t n = c / s, j = c - n * s;
+            const int r = rs_decode_column(tile + n * sf_in + j, s, s_ato, s_iof, s_lfsr);
+            if (r < 0)
+                atomicMin(&s_fail[n], (int)j);
+            else if (r > 0)
+                atomicAdd(&s_sum[n], r);
+        }
+        __syncthreads();
+        // ---- return values: sum of the per-column counts, or -1 (rschecksf.cpp:80-88) -------------
+        for (uint32_t n = tid; n < nloc; n += blockDim.x) ret[sf0 + n] = (s_fail[n] < (int)s) ? -1 : s_sum[n];
+        // ---- write back the 110*s data bytes; columns >= first failure stay untouched -------------
+        uint8_t* dst = out + sf0 * sf_out;
+        for (uint32_t n = 0; n < nloc; n++) {
+            const uint32_t fail = (uint32_t)s_fail[n];
+            const uint8_t* t = tile + n * sf_in;
+            uint8_t* d = dst + n * sf_out;
+            if (fail == s) {
+                // contiguous copy: byte head up to 4-byte alignment of d, then 32-bit words whose
+                // source bytes are gathered from two aligned shared-memory words
+                const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3);
+                const uint32_t nhead = head < sf_out ? head : (uint32_t)sf_out;
+                if (tid < nhead) d[tid] = t[tid];
+                const size_t nwords = (sf_out - nhead) / 4;
+                const uint32_t toff = (uint32_t)(reinterpret_cast<uintptr_t>(t + nhead) & 3);
+                const uint32_t* tw = reinterpret_cast<const uint32_t*>(t + nhead - toff);
+                const uint32_t sel = 0x3210u + 0x1111u * toff;
+                for (size_t w = tid; w < nwords; w += blockDim.x)
+                    reinterpret_cast<uint32_t*>(d + nhead)[w] = __byte_perm(tw[w], tw[w + 1], sel);
+                for (size_t i = nhead + nwords * 4 + tid; i < sf_out; i += blockDim.x) d[i] = t[i];
+            } else if (fail > 0) {
+                for (size_t i = tid; i < sf_out; i += blockDim.x)
+                    if ((uint32_t)(i % s) < fail) d[i] = t[i];
+            }
+        }
+    }
+}
+
+size_t rs_smem_bytes(uint32_t s, uint32_t sf_per_block) {
+    // + 16 alignment slack + 8 so the word gather may read one aligned word past the tile
+    return 4096 + 768 + 256 + 2 * sizeof(int) * (size_t)sf_per_block + 16 + (size_t)CW * s * sf_per_block + 8;
+}
+
+uint32_t rs_superframes_per_block(uint32_t s) {
+    uint32_t n = kRsThreads / s;
+    if (n >= 2) n &= ~1u;  // keep tiles 16-byte aligned in global memory
+    return n ? n : 1;
+}
+
+cudaError_t rs_upload_tables() {
+    static RsTables h;
+    uint8_t alpha[255];
+    unsigned sr = 1;
+    h.iof[0] = NN;
+    for (unsigned i = 0; i < NN; i++) {
+        h.iof[sr] = (uint8_t)i;
+        alpha[i] = (uint8_t)sr;
+        sr <<= 1;
+        if (sr & 0x100u) sr ^= 0x11Du;
+    }
+    for (unsigned i = 0; i < 768; i++) h.ato[i] = alpha[i % NN];
+    // generator g(x) = prod (x - alpha^i), i = 0..9; g[k] = coefficient of x^k
+    uint8_t g[NROOTS + 1] = {1};
+    auto mul = [&](uint8_t a, uint8_t b) -> uint8_t {
+        if (!a || !b) return 0;
+        return alpha[(h.iof[a] + h.iof[b]) % NN];
+    };
+    for (int i = 0; i < NROOTS; i++) {
+        uint8_t nx[NROOTS + 1] = {0};
+        for (int k = 0; k <= i; k++) {
+            nx[k + 1] ^= g[k];
+            nx[k] ^= mul(g[k], alpha[i]);
+        }
+        for (int k = 0; k <= i + 1; k++) g[k] = nx[k];
+    }
+    for (unsigned c = 0; c < 256; c++) {
+        uint8_t row[16] = {0};
+        for (int k = 0; k < NROOTS; k++) row[k] = mul((uint8_t)c, g[k]);
+        uint32_t w[4];
+        for (int q = 0; q < 4; q++)
+            w[q] = row[4 * q] | (row[4 * q + 1] << 8) | (row[4 * q + 2] << 16) | ((uint32_t)row[4 * q + 3] << 24);
+        h.lfsr[c] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return cudaMemcpyToSymbol(c_tables, &h, sizeof(h));
+}
+
+cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, unsigned long long nsf,
+                                  uint32_t s, int num_sms, cudaStream_t stream) {
+    if (nsf == 0) return cudaSuccess;
+    const uint32_t spb = rs_superframes_per_block(s);
+    const size_t smem = rs_smem_bytes(s, spb);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(rs_superframe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    unsigned long long nblk = (nsf + spb - 1) / spb;
+    const unsigned long long cap = (unsigned long long)num_sms * 16;
+    if (nblk > cap) nblk = cap;
+    rs_superframe_kernel<<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, nsf, s, spb);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace fec

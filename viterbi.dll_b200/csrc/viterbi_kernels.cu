@@ -1,0 +1,275 @@
+// viterbi_kernels.cu -- sm_100a kernels for the DAB mother-code Viterbi decoder.
+//
+// Replaces the hot loops of the reference: Butterfly256 / Renormalize256 / ChainBack
+// (deconvolve.cpp:334-387, 407-412, 416-435) for whole batches of frames.  Bit-exact with
+// the reference's 8-bit saturating arithmetic; the layout is redesigned for the B200 integer
+// pipes instead of 256-bit CPU vectors:
+//
+//   * one THREAD decodes TWO frames.  A 32-bit register holds the same trellis state of frame A
+//     (low half) and frame B (high half) as unsigned 16-bit lanes, so every packed min / add-min
+//     (VIADDMNMX.U16x2, full rate on the ALU pipe -- profiles/intbench_r01.jsonl) advances two
+//     frames.  64 registers hold the 64 path metrics; the butterfly network is pure register
+//     renaming (no shuffles, no shared memory, no permutes).
+//   * path metrics are kept scaled by 16 (value*16 fits 16 bits: 255*16 = 4080).  All reference
+//     operations (saturating add at 255, saturating subtract of 63, threshold 150) are linear
+//     in the metric, so scaling is exact, and it lets the branch metric be formed as
+//     (e + f) & 0x03F0 without a shift.
+//   * decisions: 64 bits per step per frame.  The sign bits of (survivor - candidate + 0x8000)
+//     are gathered with PRMT sign-replication into 4 words per step (2 frames) and streamed to
+//     a per-warp scratch area in global memory, fully coalesced (512 B per warp per step).
+//     Shared memory cannot hold them: 8 B x 3078 steps = 24.6 KB per frame would cap an SM at
+//     9 frames.
+//   * traceback runs in the same kernel, by the same thread, reading its own scratch back.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "fec_internal.h"
+
+namespace fec {
+
+namespace {
+
+// ---- code structure -------------------------------------------------------------------------
+// Encoder polynomials in the register orientation of viterbi-benchmark.cpp:64.
+__host__ __device__ constexpr unsigned kPoly(int k) { return k == 0 ? 109u : k == 1 ? 79u : k == 2 ? 83u : 109u; }
+__host__ __device__ constexpr unsigned parity8(unsigned v) {
+    v ^= v >> 4;
+    v ^= v >> 2;
+    v ^= v >> 1;
+    return v & 1u;
+}
+// Expected code bit k on the branch old-state i -> new-state 2i (the bytes of const.asm:35-49).
+__host__ __device__ constexpr unsigned tbit(int i, int k) { return parity8((2u * (unsigned)i) & kPoly(k)); }
+// Branch-metric pattern of butterfly i: bits (T0,T1,T2); T3 == T0 because polys 0 and 3 coincide.
+__host__ __device__ constexpr int pattern(int i) { return (int)(tbit(i, 0) | (tbit(i, 1) << 1) | (tbit(i, 2) << 2)); }
+
+constexpr uint32_t kSat = 0x0FF00FF0u;    // 255 * 16 per half: paddusb ceiling
+constexpr uint32_t kM63 = 0x03F003F0u;    // 63 * 16 per half
+constexpr uint32_t kSign = 0x80008000u;   // bias that keeps per-half differences borrow-free
+constexpr uint32_t kEven = 0xFFFEFFFEu;
+
+// PTX prmt in its default mode: selector nibble bit 3 replicates the sign of the selected byte.
+// (__byte_perm() masks that bit off, so it cannot be used for the sign gather.)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// Branch metrics for two frames at once (deconvolve.cpp:334-349 restated):
+//   x_k = y_k ^ T_k,  m = avg(avg(x0,x1), avg(x2,x3)) >> 2  with avg(a,b) = (a+b+1)>>1.
+// With a = (x0+x1+1)>>1 and b = (x2+x3+1)>>1:  16*m = (2a + 2b + 2) & 0x3F0.
+// x ^ 0xFF = 255 - x, so the four (T0,T1) cases of x0+x1+1 are linear in y0+y1 or y0-y1.
+// wA / wB: the four soft symbols of one trellis step of frame A / frame B.
+__device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_t (&bm)[8], uint32_t (&bmm)[8]) {
+    const uint32_t p01 = __byte_perm(wA, wB, 0x5140);  // A0 B0 A1 B1
+    const uint32_t p23 = __byte_perm(wA, wB, 0x7362);  // A2 B2 A3 B3
+    const uint32_t y0 = __byte_perm(p01, 0u, 0x4140), y1 = __byte_perm(p01, 0u, 0x4342);
+    const uint32_t y2 = __byte_perm(p23, 0u, 0x4140), y3 = __byte_perm(p23, 0u, 0x4342);
+    const uint32_t u01 = y0 + y1, v01 = y0 - y1 + 0x01020102u;  // y0-y1+256 (+2 rounding term)
+    const uint32_t u23 = y2 + y3, v23 = y2 - y3 + 0x01000100u;
+    uint32_t e[2][2], f[2][2];  // e[T0][T1] = 2a+2, f[T2][T0] = 2b
+    e[0][0] = (u01 + 0x00030003u) & kEven;
+    e[1][1] = (0x02010201u - u01) & kEven;
+    e[0][1] = v01 & kEven;
+    e[1][0] = (0x02040204u - v01) & kEven;
+    f[0][0] = (u23 + 0x00010001u) & kEven;
+    f[1][1] = (0x01FF01FFu - u23) & kEven;
+    f[0][1] = v23 & kEven;
+    f[1][0] = (0x02000200u - v23) & kEven;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int t0 = p & 1, t1 = (p >> 1) & 1, t2 = (p >> 2) & 1;
+        bm[p] = (e[t0][t1] + f[t2][t0]) & kM63;
+        bmm[p] = kM63 - bm[p];
+    }
+}
+
+// One trellis step for two frames: old metrics M -> new metrics N, 4 decision words.
+// Per butterfly i (old states i, i+32 -> new states 2i, 2i+1), with m = bm[pattern(i)]:
+//   t1 = min(M[i+32] + (63-m), 255)        survivor candidate through the upper branch
+//   N[2i] = min(M[i] + m, t1)               == min(sat(M[i]+m), sat(M[i+32]+63-m))
+//   decision(2i) = (t1 <= sat(M[i]+m))      == (N[2i] == t1): ties choose predecessor i+32
+// and symmetrically for 2i+1 (deconvolve.cpp:352-359).
+// Decision words: word q = butterflies 8q..8q+7; byte 0/1 = frame A even/odd new state,
+// byte 2/3 = frame B even/odd; bit (i & 7).
+__device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)[64], uint32_t wA, uint32_t wB) {
+    uint32_t bm[8], bmm[8];
+    branch_metrics(wA, wB, bm, bmm);
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        constexpr int kPat[32] = {pattern(0),  pattern(1),  pattern(2),  pattern(3),  pattern(4),  pattern(5),  pattern(6),
+                                  pattern(7),  pattern(8),  pattern(9),  pattern(10), pattern(11), pattern(12), pattern(13),
+                                  pattern(14), pattern(15), pattern(16), pattern(17), pattern(18), pattern(19), pattern(20),
+                                  pattern(21), pattern(22), pattern(23), pattern(24), pattern(25), pattern(26), pattern(27),
+                                  pattern(28), pattern(29), pattern(30), pattern(31)};
+        const uint32_t m = bm[kPat[i]], mm = bmm[kPat[i]];
+        const uint32_t a = M[i], b = M[i + 32];
+        const uint32_t t1 = __viaddmin_u16x2(b, mm, kSat);
+        const uint32_t ne = __viaddmin_u16x2(a, m, t1);
+        const uint32_t de = ne + kSign - t1;  // bit 15 / 31 set iff ne == t1 (ne <= t1, so no borrow)
+        const uint32_t t3 = __viaddmin_u16x2(b, m, kSat);
+        const uint32_t no = __viaddmin_u16x2(a, mm, t3);
+        const uint32_t dd = no + kSign - t3;
+        N[2 * i] = ne;
+        N[2 * i + 1] = no;
+        // sign-replicating permute: bytes (A even, A odd, B even, B odd) become 0x00 / 0xFF
+        const uint32_t sg = prmt(de, dd, 0xFBD9u);
+        acc[i >> 3] |= sg & (0x01010101u << (i & 7));
+    }
+    return make_uint4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// Renormalize256 (deconvolve.cpp:407-412): if metric[state 0] > 150 subtract 63 with saturation at 0
+// from all 64 metrics -- decided per frame, i.e. per 16-bit half.
+__device__ __forceinline__ void renormalize(uint32_t (&M)[64]) {
+    // bit 15 of (M0 + 0x7FFF - 2400) is set iff M0 > 2400 (= 150 * 16)
+    const uint32_t hit = ((M[0] + 0x769F769Fu) >> 15) & 0x00010001u;
+    const uint32_t neg = hit * 0xFC10u;  // -1008 (= -63 * 16) in the halves that renormalise, else 0
+#pragma unroll
+    // relu(max(M + neg, neg)) == max(M - 63*16, 0): the .relu form needs no zero operand
+    for (int s = 0; s < 64; s++) M[s] = __viaddmax_s16x2_relu(M[s], neg, neg);
+}
+
+__device__ __forceinline__ uint32_t pick(const uint4& w, uint32_t q) {
+    const uint32_t lo = (q & 1u) ? w.y : w.x, hi = (q & 1u) ? w.w : w.z;
+    return (q & 2u) ? hi : lo;
+}
+
+// ChainBack (deconvolve.cpp:416-435) for the two frames of this thread.  `es` mirrors the
+// reference's 8-bit EndState register (state << 2).
+template <bool kWordStores>
+__device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_t framebits, uint8_t* outA,
+                                          uint8_t* outB, bool liveA, bool liveB) {
+    uint32_t esA = 0, esB = 0, wordA = 0, wordB = 0;
+    for (int t = (int)framebits - 1; t >= 0; t--) {
+        const uint4 w = dec[(size_t)(t + 6) * 32];
+        {
+            const uint32_t s = esA >> 2;  // state of frame A
+            const uint32_t k = (pick(w, s >> 4) >> (((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
+            esA = (esA >> 1) | (k << 7);
+        }
+        {
+            const uint32_t s = esB >> 2;
+            const uint32_t k = (pick(w, s >> 4) >> (16u + ((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
+            esB = (esB >> 1) | (k << 7);
+        }
+        if ((t & 7) == 0) {
+            if (kWordStores) {
+                wordA = (wordA << 8) | esA;
+                wordB = (wordB << 8) | esB;
+                if ((t & 31) == 0) {
+                    if (liveA) *reinterpret_cast<uint32_t*>(outA + (t >> 3)) = wordA;
+                    if (liveB) *reinterpret_cast<uint32_t*>(outB + (t >> 3)) = wordB;
+                }
+            } else {
+                if (liveA) outA[t >> 3] = (uint8_t)esA;
+                if (liveB) outB[t >> 3] = (uint8_t)esB;
+            }
+        }  // bytes are final at t % 8 == 0 (the reference stores every step; the last store wins)
+    }
+}
+
+}  // namespace
+
+// Throughput kernel: each warp decodes groups of 64 frames (lane L: frames 64g+L and 64g+32+L).
+// scratch: per warp `steps` x 32 uint4.
+template <bool kWordStores>
+__global__ void __launch_bounds__(kVitThreads, kVitMinBlocks)
+viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint4* __restrict__ scratch,
+                    unsigned long long nframes, uint32_t framebits) {
+    const uint32_t steps = framebits + 6;  // framebits is even: 2 * ((F + 6) / 2) == F + 6
+    const size_t rowbytes = (size_t)4 * steps, outbytes = (framebits + 7) / 8;
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long ngroups = (nframes + 63) / 64;
+    uint4* dec = scratch + warp * (size_t)steps * 32 + lane;
+
+    for (unsigned long long g = warp; g < ngroups; g += nwarps) {
+        const unsigned long long fA = g * 64 + lane, fB = fA + 32;
+        const bool liveA = fA < nframes, liveB = fB < nframes;
+        const uint2* rowA = reinterpret_cast<const uint2*>(syms + (liveA ? fA : nframes - 1) * rowbytes);
+        const uint2* rowB = reinterpret_cast<const uint2*>(syms + (liveB ? fB : nframes - 1) * rowbytes);
+
+        uint32_t X[64], Y[64];
+        X[0] = 0u;  // Locals256: start state 0 has metric 0, all others 63 (deconvolve.cpp:130-132)
+#pragma unroll
+        for (int s = 1; s < 64; s++) X[s] = kM63;
+
+        uint32_t t = 0;
+        // 6 steps per iteration: after six steps the butterfly renaming of the 64 metric registers
+        // returns to the identity, so the loop carries no register moves.
+        for (; t + 6 <= steps; t += 6) {
+            const uint2 a0 = __ldg(rowA + (t >> 1)), a1 = __ldg(rowA + (t >> 1) + 1), a2 = __ldg(rowA + (t >> 1) + 2);
+            const uint2 b0 = __ldg(rowB + (t >> 1)), b1 = __ldg(rowB + (t >> 1) + 1), b2 = __ldg(rowB + (t >> 1) + 2);
+            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x);
+            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y);
+            renormalize(X);
+            dec[(size_t)(t + 2) * 32] = acs_step(X, Y, a1.x, b1.x);
+            dec[(size_t)(t + 3) * 32] = acs_step(Y, X, a1.y, b1.y);
+            renormalize(X);
+            dec[(size_t)(t + 4) * 32] = acs_step(X, Y, a2.x, b2.x);
+            dec[(size_t)(t + 5) * 32] = acs_step(Y, X, a2.y, b2.y);
+            renormalize(X);
+        }
+        for (; t + 2 <= steps; t += 2) {  // framebits not a multiple of 6
+            const uint2 a0 = __ldg(rowA + (t >> 1));
+            const uint2 b0 = __ldg(rowB + (t >> 1));
+            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x);
+            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y);
+            renormalize(X);
+        }
+        traceback<kWordStores>(dec, framebits, out + fA * outbytes, out + fB * outbytes, liveA, liveB);
+    }
+}
+
+// u32 -> u8 compaction for the QIRX one-word-per-symbol layout (low byte only, deconvolve.cpp:219-228)
+__global__ void __launch_bounds__(256) compact_symbols_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ outw,
+                                                              size_t nquads) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(in + i);
+        outw[i] = (v.x & 0xFFu) | ((v.y & 0xFFu) << 8) | ((v.z & 0xFFu) << 16) | (v.w << 24);
+    }
+}
+
+size_t viterbi_scratch_bytes(int grid_blocks, uint32_t framebits) {
+    const size_t warps = (size_t)grid_blocks * (kVitThreads / 32);
+    return warps * (size_t)(framebits + 6) * 32 * sizeof(uint4);
+}
+
+int viterbi_grid_blocks(int num_sms, unsigned long long nframes) {
+    const unsigned long long warps_needed = (nframes + 63) / 64;
+    const unsigned long long blocks_needed = (warps_needed + (kVitThreads / 32) - 1) / (kVitThreads / 32);
+    const unsigned long long resident = (unsigned long long)num_sms * kVitMinBlocks;
+    return (int)(blocks_needed < resident ? blocks_needed : resident);
+}
+
+cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_scratch, unsigned long long nframes,
+                                uint32_t framebits, int grid_blocks, cudaStream_t stream) {
+    if (nframes == 0) return cudaSuccess;
+    if (framebits % 32 == 0)
+        viterbi_pair_kernel<true><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint4*)d_scratch, nframes,
+                                                                            framebits);
+    else
+        viterbi_pair_kernel<false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint4*)d_scratch, nframes,
+                                                                             framebits);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t nsymbols, int num_sms,
+                                   cudaStream_t stream) {
+    if (nsymbols == 0) return cudaSuccess;
+    const size_t nquads = nsymbols / 4;  // symbol count per frame is a multiple of 4
+    size_t blocks = (nquads + 255) / 256;
+    const size_t cap = (size_t)num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    compact_symbols_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)d_in, (uint32_t*)d_out, nquads);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace fec
