@@ -173,10 +173,10 @@ int vit_host(unsigned framebits, const void* syms, bool is_u32, size_t n, uint8_
 
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
     const size_t in_row = nsym * (is_u32 ? 4 : 1);
-    // chunk: about 64 MiB of u8 symbols, at least one full wave of the kernel grid
-    size_t chunk = (64u << 20) / nsym;
-    const size_t wave = (size_t)st->num_sms * kVitMinBlocks * (kVitThreads / 32) * 64;
-    if (chunk < wave) chunk = wave;
+    // chunk: about 32 MiB of u8 symbols (a multiple of the 64-frame warp group) so that the H2D copy
+    // of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap on the kPipe streams
+    size_t chunk = ((32u << 20) / nsym) & ~(size_t)63;
+    if (chunk < 64) chunk = 64;
     if (chunk > n) chunk = n;
     int rc = FEC_OK;
     size_t done = 0;

@@ -7,10 +7,11 @@
 
 namespace fec {
 
-// Viterbi throughput kernel launch shape: 128 threads (4 warps, one per SM sub-partition) and
-// up to kVitMinBlocks resident blocks per SM.
-constexpr int kVitThreads = 128;
-constexpr int kVitMinBlocks = 3;
+// Viterbi throughput kernel launch shape: one warp per block (64 frames in flight per block),
+// up to kVitMinBlocks resident blocks per SM (register-limited: 12 x 32 x 168 registers).
+constexpr int kVitThreads = 32;
+constexpr int kVitMinBlocks = 12;
+constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision area 256-byte aligned
 
 constexpr int kRsThreads = 128;
 

@@ -174,21 +174,24 @@ __device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_
 
 }  // namespace
 
-// Throughput kernel: each warp decodes groups of 64 frames (lane L: frames 64g+L and 64g+32+L).
-// scratch: per warp `steps` x 32 uint4.
+// Throughput kernel.  One warp per block; a warp decodes groups of 64 frames (lane L: frames
+// 64g+L and 64g+32+L).  The grid is persistent (as many warps as fit on the device) and groups are
+// handed out dynamically through a ticket counter so that uneven progress does not leave SM
+// sub-partitions idle at the tail.  scratch: [ticket counter, 256 B][per warp: steps x 32 uint4].
 template <bool kWordStores>
 __global__ void __launch_bounds__(kVitThreads, kVitMinBlocks)
-viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint4* __restrict__ scratch,
+viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
                     unsigned long long nframes, uint32_t framebits) {
     const uint32_t steps = framebits + 6;  // framebits is even: 2 * ((F + 6) / 2) == F + 6
     const size_t rowbytes = (size_t)4 * steps, outbytes = (framebits + 7) / 8;
     const uint32_t lane = threadIdx.x & 31u;
-    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long warp = blockIdx.x, nwarps = gridDim.x;
     const unsigned long long ngroups = (nframes + 63) / 64;
-    uint4* dec = scratch + warp * (size_t)steps * 32 + lane;
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(scratch);
+    uint4* dec = reinterpret_cast<uint4*>(scratch + kVitScratchHeader) + warp * (size_t)steps * 32 + lane;
 
-    for (unsigned long long g = warp; g < ngroups; g += nwarps) {
+    unsigned long long g = warp;  // first group is static, later ones come from the ticket counter
+    while (g < ngroups) {
         const unsigned long long fA = g * 64 + lane, fB = fA + 32;
         const bool liveA = fA < nframes, liveB = fB < nframes;
         const uint2* rowA = reinterpret_cast<const uint2*>(syms + (liveA ? fA : nframes - 1) * rowbytes);
@@ -223,6 +226,10 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
             renormalize(X);
         }
         traceback<kWordStores>(dec, framebits, out + fA * outbytes, out + fB * outbytes, liveA, liveB);
+
+        unsigned long long next = 0;
+        if (lane == 0) next = nwarps + atomicAdd(ticket, 1ull);
+        g = __shfl_sync(0xffffffffu, next, 0);
     }
 }
 
@@ -236,25 +243,25 @@ __global__ void __launch_bounds__(256) compact_symbols_kernel(const uint4* __res
 }
 
 size_t viterbi_scratch_bytes(int grid_blocks, uint32_t framebits) {
-    const size_t warps = (size_t)grid_blocks * (kVitThreads / 32);
-    return warps * (size_t)(framebits + 6) * 32 * sizeof(uint4);
+    return kVitScratchHeader + (size_t)grid_blocks * (size_t)(framebits + 6) * 32 * sizeof(uint4);
 }
 
 int viterbi_grid_blocks(int num_sms, unsigned long long nframes) {
-    const unsigned long long warps_needed = (nframes + 63) / 64;
-    const unsigned long long blocks_needed = (warps_needed + (kVitThreads / 32) - 1) / (kVitThreads / 32);
+    const unsigned long long groups = (nframes + 63) / 64;
     const unsigned long long resident = (unsigned long long)num_sms * kVitMinBlocks;
-    return (int)(blocks_needed < resident ? blocks_needed : resident);
+    return (int)(groups < resident ? groups : resident);
 }
 
 cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_scratch, unsigned long long nframes,
                                 uint32_t framebits, int grid_blocks, cudaStream_t stream) {
     if (nframes == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, kVitScratchHeader, stream);  // ticket counter
+    if (e != cudaSuccess) return e;
     if (framebits % 32 == 0)
-        viterbi_pair_kernel<true><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint4*)d_scratch, nframes,
+        viterbi_pair_kernel<true><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
                                                                             framebits);
     else
-        viterbi_pair_kernel<false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint4*)d_scratch, nframes,
+        viterbi_pair_kernel<false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
                                                                              framebits);
     count_launch();
     return cudaGetLastError();

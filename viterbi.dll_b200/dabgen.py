@@ -215,3 +215,36 @@ def make_superframes(n: int, s: int, seed: int, max_err: int = 7):
     rx = rs_inject_errors(cw, nerr, rng)
     payload = np.ascontiguousarray(msg.reshape(n, s, RS_K).transpose(0, 2, 1)).reshape(n, RS_K * s)
     return rs_interleave(rx, s), payload, nerr.reshape(n, s)
+
+
+def make_superframes_torch(n: int, s: int, seed: int, device, max_err: int = 7, chunk: int = 1 << 18):
+    """Device-side version of make_superframes (benchmark inputs): -> (received [n,120*s] u8 tensor,
+    errors per codeword [n,s])."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    exp = torch.from_numpy(_EXP.astype(np.int64)).to(device)
+    log = torch.from_numpy(_LOG.astype(np.int64)).to(device)
+    ghi_log = log[torch.from_numpy(_GEN[RS_T2 - 1 :: -1].astype(np.int64)).to(device)]  # g_9..g_0 (all non-zero)
+    ncw = n * s
+    rx = torch.empty((ncw, RS_N), dtype=torch.uint8, device=device)
+    nerr_all = torch.empty((ncw,), dtype=torch.int64, device=device)
+    for lo in range(0, ncw, chunk):
+        m = min(chunk, ncw - lo)
+        msg = torch.randint(0, 256, (m, RS_K), generator=g, device=device, dtype=torch.int64)
+        reg = torch.zeros((m, RS_T2), dtype=torch.int64, device=device)
+        for k in range(RS_K):
+            fb = msg[:, k] ^ reg[:, 0]
+            reg = torch.cat((reg[:, 1:], torch.zeros((m, 1), dtype=torch.int64, device=device)), dim=1)
+            prod = exp[(log[fb][:, None] + ghi_log[None, :]) % 255]
+            reg ^= torch.where(fb[:, None] == 0, torch.zeros_like(prod), prod)
+        cw = torch.cat((msg, reg), dim=1)
+        nerr = torch.randint(0, max_err + 1, (m,), generator=g, device=device)
+        order = torch.argsort(torch.rand((m, RS_N), generator=g, device=device), dim=1)  # rank of each position
+        vals = torch.randint(1, 256, (m, RS_N), generator=g, device=device, dtype=torch.int64)
+        cw ^= torch.where(order < nerr[:, None], vals, torch.zeros_like(vals))
+        rx[lo : lo + m] = cw.to(torch.uint8)
+        nerr_all[lo : lo + m] = nerr
+    rx = rx.reshape(n, s, RS_N).transpose(1, 2).contiguous().reshape(n, RS_N * s)
+    return rx, nerr_all.reshape(n, s)
