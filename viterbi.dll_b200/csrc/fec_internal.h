@@ -8,9 +8,9 @@
 namespace fec {
 
 // Viterbi throughput kernel launch shape: one warp per block (64 frames in flight per block),
-// up to kVitMinBlocks resident blocks per SM (register-limited: 12 x 32 x 168 registers).
+// up to kVitMinBlocks resident blocks per SM (register-limited: 2 warps per SM sub-partition x 255 registers).
 constexpr int kVitThreads = 32;
-constexpr int kVitMinBlocks = 12;
+constexpr int kVitMinBlocks = 8;
 constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision area 256-byte aligned
 
 constexpr int kRsThreads = 128;

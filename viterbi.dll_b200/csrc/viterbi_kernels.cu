@@ -139,36 +139,77 @@ __device__ __forceinline__ uint32_t pick(const uint4& w, uint32_t q) {
 }
 
 // ChainBack (deconvolve.cpp:416-435) for the two frames of this thread.  `es` mirrors the
-// reference's 8-bit EndState register (state << 2).
+// reference's 8-bit EndState register (state << 2); the decoded byte is final when t % 8 == 0
+// (the reference stores on every step, the last store wins).
+struct TraceState {
+    uint32_t esA = 0, esB = 0, wordA = 0, wordB = 0;
+};
+
+template <bool kWordStores>
+__device__ __forceinline__ void trace_step(TraceState& st, const uint4& w, int t, uint8_t* outA, uint8_t* outB,
+                                           bool liveA, bool liveB) {
+    {
+        const uint32_t s = st.esA >> 2;  // state of frame A
+        const uint32_t k = (pick(w, s >> 4) >> (((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
+        st.esA = (st.esA >> 1) | (k << 7);
+    }
+    {
+        const uint32_t s = st.esB >> 2;
+        const uint32_t k = (pick(w, s >> 4) >> (16u + ((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
+        st.esB = (st.esB >> 1) | (k << 7);
+    }
+    if ((t & 7) == 0) {
+        if (kWordStores) {
+            st.wordA = (st.wordA << 8) | st.esA;
+            st.wordB = (st.wordB << 8) | st.esB;
+            if ((t & 31) == 0) {
+                if (liveA) *reinterpret_cast<uint32_t*>(outA + (t >> 3)) = st.wordA;
+                if (liveB) *reinterpret_cast<uint32_t*>(outB + (t >> 3)) = st.wordB;
+            }
+        } else {
+            if (liveA) outA[t >> 3] = (uint8_t)st.esA;
+            if (liveB) outB[t >> 3] = (uint8_t)st.esB;
+        }
+    }
+}
+
+constexpr int kTraceChunk = 16;  // decision words prefetched per chunk (2 chunks in flight)
+
+__device__ __forceinline__ void trace_load(uint4 (&buf)[kTraceChunk], const uint4* __restrict__ dec, int tb) {
+#pragma unroll
+    for (int j = 0; j < kTraceChunk; j++) buf[j] = dec[(size_t)(tb + j + 6) * 32];
+}
+
+template <bool kWordStores>
+__device__ __forceinline__ void trace_chunk(TraceState& st, const uint4 (&buf)[kTraceChunk], int tb, uint8_t* outA,
+                                            uint8_t* outB, bool liveA, bool liveB) {
+#pragma unroll
+    for (int j = kTraceChunk - 1; j >= 0; j--) trace_step<kWordStores>(st, buf[j], tb + j, outA, outB, liveA, liveB);
+}
+
+// The state recursion is serial, but the decision words it consumes do not depend on it: they are
+// fetched a chunk ahead (double-buffered in the registers the path metrics no longer need), so the
+// traceback runs at ALU latency instead of one global-memory round trip per step.
 template <bool kWordStores>
 __device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_t framebits, uint8_t* outA,
                                           uint8_t* outB, bool liveA, bool liveB) {
-    uint32_t esA = 0, esB = 0, wordA = 0, wordB = 0;
-    for (int t = (int)framebits - 1; t >= 0; t--) {
-        const uint4 w = dec[(size_t)(t + 6) * 32];
-        {
-            const uint32_t s = esA >> 2;  // state of frame A
-            const uint32_t k = (pick(w, s >> 4) >> (((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
-            esA = (esA >> 1) | (k << 7);
-        }
-        {
-            const uint32_t s = esB >> 2;
-            const uint32_t k = (pick(w, s >> 4) >> (16u + ((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
-            esB = (esB >> 1) | (k << 7);
-        }
-        if ((t & 7) == 0) {
-            if (kWordStores) {
-                wordA = (wordA << 8) | esA;
-                wordB = (wordB << 8) | esB;
-                if ((t & 31) == 0) {
-                    if (liveA) *reinterpret_cast<uint32_t*>(outA + (t >> 3)) = wordA;
-                    if (liveB) *reinterpret_cast<uint32_t*>(outB + (t >> 3)) = wordB;
-                }
-            } else {
-                if (liveA) outA[t >> 3] = (uint8_t)esA;
-                if (liveB) outB[t >> 3] = (uint8_t)esB;
-            }
-        }  // bytes are final at t % 8 == 0 (the reference stores every step; the last store wins)
+    TraceState st;
+    int t = (int)framebits - 1;
+    const int head = (int)(framebits % kTraceChunk);
+    for (int i = 0; i < head; i++, t--) trace_step<kWordStores>(st, dec[(size_t)(t + 6) * 32], t, outA, outB, liveA, liveB);
+    int tb = t + 1 - kTraceChunk;  // base of the next full chunk (a multiple of kTraceChunk)
+    if (tb < 0) return;
+    uint4 bufA[kTraceChunk], bufB[kTraceChunk];
+    trace_load(bufA, dec, tb);
+    while (true) {
+        if (tb >= kTraceChunk) trace_load(bufB, dec, tb - kTraceChunk);
+        trace_chunk<kWordStores>(st, bufA, tb, outA, outB, liveA, liveB);
+        tb -= kTraceChunk;
+        if (tb < 0) break;
+        if (tb >= kTraceChunk) trace_load(bufA, dec, tb - kTraceChunk);
+        trace_chunk<kWordStores>(st, bufB, tb, outA, outB, liveA, liveB);
+        tb -= kTraceChunk;
+        if (tb < 0) break;
     }
 }
 
@@ -204,10 +245,20 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
 
         uint32_t t = 0;
         // 6 steps per iteration: after six steps the butterfly renaming of the 64 metric registers
-        // returns to the identity, so the loop carries no register moves.
+        // returns to the identity, so the loop carries no register moves.  The 48 symbol bytes of the
+        // next iteration are fetched while this one computes.
+        uint2 a0, a1, a2, b0, b1, b2;
+        if (steps >= 6) {
+            a0 = __ldg(rowA), a1 = __ldg(rowA + 1), a2 = __ldg(rowA + 2);
+            b0 = __ldg(rowB), b1 = __ldg(rowB + 1), b2 = __ldg(rowB + 2);
+        }
         for (; t + 6 <= steps; t += 6) {
-            const uint2 a0 = __ldg(rowA + (t >> 1)), a1 = __ldg(rowA + (t >> 1) + 1), a2 = __ldg(rowA + (t >> 1) + 2);
-            const uint2 b0 = __ldg(rowB + (t >> 1)), b1 = __ldg(rowB + (t >> 1) + 1), b2 = __ldg(rowB + (t >> 1) + 2);
+            uint2 na0 = a0, na1 = a1, na2 = a2, nb0 = b0, nb1 = b1, nb2 = b2;
+            if (t + 12 <= steps) {
+                const uint32_t q = (t >> 1) + 3;
+                na0 = __ldg(rowA + q), na1 = __ldg(rowA + q + 1), na2 = __ldg(rowA + q + 2);
+                nb0 = __ldg(rowB + q), nb1 = __ldg(rowB + q + 1), nb2 = __ldg(rowB + q + 2);
+            }
             dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x);
             dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y);
             renormalize(X);
@@ -217,6 +268,7 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
             dec[(size_t)(t + 4) * 32] = acs_step(X, Y, a2.x, b2.x);
             dec[(size_t)(t + 5) * 32] = acs_step(Y, X, a2.y, b2.y);
             renormalize(X);
+            a0 = na0, a1 = na1, a2 = na2, b0 = nb0, b1 = nb1, b2 = nb2;
         }
         for (; t + 2 <= steps; t += 2) {  // framebits not a multiple of 6
             const uint2 a0 = __ldg(rowA + (t >> 1));
