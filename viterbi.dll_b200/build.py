@@ -12,10 +12,15 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libviterbi_b200.so")
-SOURCES = ["viterbi_kernels.cu", "rs_kernels.cu", "fec_api.cu"]
+# per-source extra flags.  viterbi_kernels.cu is compiled with ptxas -O1: at -O2/-O3 the ptxas
+# scheduler hoists the packed-min instructions far ahead of the predicated IMADs that consume their
+# predicate outputs, runs out of the 7 predicate registers and spills predicates through LOP3 pairs
+# (2642 vs 607 LOP3 in the loop body); -O1 keeps program order, which is already interleaved.
+SOURCES = {"viterbi_kernels.cu": ["-Xptxas", "-O1"], "rs_kernels.cu": [], "fec_api.cu": []}
 HEADERS = [os.path.join(CSRC, "fec_internal.h"), os.path.join(os.path.dirname(HERE), "include", "viterbi_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-cudart", "static"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def nvcc() -> str | None:
@@ -36,7 +41,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     cc = nvcc()
     if cc is None:
         raise RuntimeError("nvcc not found: cannot build libviterbi_b200.so (there is no CPU fallback)")
-    cmd = [cc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = []
+    for src, extra in SOURCES.items():
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        cmd = [cc] + ARCH_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    cmd = [cc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -14,9 +14,11 @@
 //     operations (saturating add at 255, saturating subtract of 63, threshold 150) are linear
 //     in the metric, so scaling is exact, and it lets the branch metric be formed as
 //     (e + f) & 0x03F0 without a shift.
-//   * decisions: 64 bits per step per frame.  The sign bits of (survivor - candidate + 0x8000)
-//     are gathered with PRMT sign-replication into 4 words per step (2 frames) and streamed to
-//     a per-warp scratch area in global memory, fully coalesced (512 B per warp per step).
+//   * decisions: 64 bits per step per frame.  The survivor select is a packed min that also
+//     returns one predicate per frame (VIMNMX.U16x2 with predicate outputs); each predicate adds
+//     its decision bit to a per-frame 64-bit word with a predicated IMAD, which runs on the FMA
+//     pipe and so overlaps the ALU-pipe min/add-min work.  The words are streamed to a per-warp
+//     scratch area in global memory, fully coalesced (512 B per warp per step).
 //     Shared memory cannot hold them: 8 B x 3078 steps = 24.6 KB per frame would cap an SM at
 //     9 frames.
 //   * traceback runs in the same kernel, by the same thread, reading its own scratch back.
@@ -46,15 +48,33 @@ __host__ __device__ constexpr int pattern(int i) { return (int)(tbit(i, 0) | (tb
 
 constexpr uint32_t kSat = 0x0FF00FF0u;    // 255 * 16 per half: paddusb ceiling
 constexpr uint32_t kM63 = 0x03F003F0u;    // 63 * 16 per half
-constexpr uint32_t kSign = 0x80008000u;   // bias that keeps per-half differences borrow-free
 constexpr uint32_t kEven = 0xFFFEFFFEu;
 
-// PTX prmt in its default mode: selector nibble bit 3 replicates the sign of the selected byte.
-// (__byte_perm() masks that bit off, so it cannot be used for the sign gather.)
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+// a + b on the FMA pipe: IMAD with a multiplier the compiler cannot fold (`one` is a kernel argument
+// that is always 1).  ptxas would otherwise emit IADD3 and put the add on the already saturated ALU pipe.
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) {
     uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
     return d;
+}
+
+// ne = min(t, m0) per 16-bit half, and for each half whose minimum is t (ties included) add `bit` to
+// that frame's decision word.  ptxas fuses the min + setp pattern into one VIMNMX.U16x2 with two
+// predicate outputs (the same pattern __vibmin_u16x2 uses) and keeps the adds as predicated IMADs.
+__device__ __forceinline__ uint32_t min_decide(uint32_t t, uint32_t m0, uint32_t& decA, uint32_t& decB, uint32_t one,
+                                               uint32_t bit) {
+    uint32_t ne;
+    asm("{.reg .pred pu, pv; .reg .u16 rs0, rs1, rs2, rs3;\n\t"
+        "min.u16x2 %0, %3, %4;\n\t"
+        "mov.b32 {rs0, rs1}, %0;\n\t"
+        "mov.b32 {rs2, rs3}, %3;\n\t"
+        "setp.eq.u16 pv, rs0, rs2;\n\t"
+        "setp.eq.u16 pu, rs1, rs3;\n\t"
+        "@pv mad.lo.u32 %1, %5, %6, %1;\n\t"
+        "@pu mad.lo.u32 %2, %5, %6, %2;}\n\t"
+        : "=r"(ne), "+r"(decA), "+r"(decB)
+        : "r"(t), "r"(m0), "r"(one), "r"(bit));
+    return ne;
 }
 
 // Branch metrics for two frames at once (deconvolve.cpp:334-349 restated):
@@ -62,7 +82,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // With a = (x0+x1+1)>>1 and b = (x2+x3+1)>>1:  16*m = (2a + 2b + 2) & 0x3F0.
 // x ^ 0xFF = 255 - x, so the four (T0,T1) cases of x0+x1+1 are linear in y0+y1 or y0-y1.
 // wA / wB: the four soft symbols of one trellis step of frame A / frame B.
-__device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_t (&bm)[8], uint32_t (&bmm)[8]) {
+__device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_t (&bm)[8], uint32_t (&bmm)[8],
+                                               uint32_t one) {
     const uint32_t p01 = __byte_perm(wA, wB, 0x5140);  // A0 B0 A1 B1
     const uint32_t p23 = __byte_perm(wA, wB, 0x7362);  // A2 B2 A3 B3
     const uint32_t y0 = __byte_perm(p01, 0u, 0x4140), y1 = __byte_perm(p01, 0u, 0x4342);
@@ -81,23 +102,24 @@ __device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_
 #pragma unroll
     for (int p = 0; p < 8; p++) {
         const int t0 = p & 1, t1 = (p >> 1) & 1, t2 = (p >> 2) & 1;
-        bm[p] = (e[t0][t1] + f[t2][t0]) & kM63;
+        bm[p] = fma_add(e[t0][t1], f[t2][t0], one) & kM63;
         bmm[p] = kM63 - bm[p];
     }
 }
 
 // One trellis step for two frames: old metrics M -> new metrics N, 4 decision words.
 // Per butterfly i (old states i, i+32 -> new states 2i, 2i+1), with m = bm[pattern(i)]:
-//   t1 = min(M[i+32] + (63-m), 255)        survivor candidate through the upper branch
-//   N[2i] = min(M[i] + m, t1)               == min(sat(M[i]+m), sat(M[i+32]+63-m))
-//   decision(2i) = (t1 <= sat(M[i]+m))      == (N[2i] == t1): ties choose predecessor i+32
+//   t1 = min(M[i+32] + (63-m), 255)        candidate through the upper branch, saturated
+//   N[2i] = min(t1, M[i] + m)               == min(sat(M[i]+m), sat(M[i+32]+63-m)) because t1 <= 255
+//   decision(2i) = (t1 <= M[i] + m)         == (N[2i] == t1): ties choose predecessor i+32
 // and symmetrically for 2i+1 (deconvolve.cpp:352-359).
-// Decision words: word q = butterflies 8q..8q+7; byte 0/1 = frame A even/odd new state,
-// byte 2/3 = frame B even/odd; bit (i & 7).
-__device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)[64], uint32_t wA, uint32_t wB) {
+// Decision words (the reference's decision_t layout, viterbi.h:90-92): x,y = frame A bits 0-31,
+// 32-63; z,w = frame B; bit s = decision of new state s.
+__device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)[64], uint32_t wA, uint32_t wB,
+                                          uint32_t one) {
     uint32_t bm[8], bmm[8];
-    branch_metrics(wA, wB, bm, bmm);
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+    branch_metrics(wA, wB, bm, bmm, one);
+    uint32_t dA[2] = {0u, 0u}, dB[2] = {0u, 0u};
 #pragma unroll
     for (int i = 0; i < 32; i++) {
         constexpr int kPat[32] = {pattern(0),  pattern(1),  pattern(2),  pattern(3),  pattern(4),  pattern(5),  pattern(6),
@@ -108,18 +130,14 @@ __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)
         const uint32_t m = bm[kPat[i]], mm = bmm[kPat[i]];
         const uint32_t a = M[i], b = M[i + 32];
         const uint32_t t1 = __viaddmin_u16x2(b, mm, kSat);
-        const uint32_t ne = __viaddmin_u16x2(a, m, t1);
-        const uint32_t de = ne + kSign - t1;  // bit 15 / 31 set iff ne == t1 (ne <= t1, so no borrow)
         const uint32_t t3 = __viaddmin_u16x2(b, m, kSat);
-        const uint32_t no = __viaddmin_u16x2(a, mm, t3);
-        const uint32_t dd = no + kSign - t3;
-        N[2 * i] = ne;
-        N[2 * i + 1] = no;
-        // sign-replicating permute: bytes (A even, A odd, B even, B odd) become 0x00 / 0xFF
-        const uint32_t sg = prmt(de, dd, 0xFBD9u);
-        acc[i >> 3] |= sg & (0x01010101u << (i & 7));
+        const uint32_t m0 = fma_add(a, m, one);
+        const uint32_t m2 = fma_add(a, mm, one);
+        const int w = i >> 4;  // new states 2i, 2i+1 live in decision word (2i) / 32
+        N[2 * i] = min_decide(t1, m0, dA[w], dB[w], one, 1u << ((2 * i) & 31));
+        N[2 * i + 1] = min_decide(t3, m2, dA[w], dB[w], one, 1u << ((2 * i + 1) & 31));
     }
-    return make_uint4(acc[0], acc[1], acc[2], acc[3]);
+    return make_uint4(dA[0], dA[1], dB[0], dB[1]);
 }
 
 // Renormalize256 (deconvolve.cpp:407-412): if metric[state 0] > 150 subtract 63 with saturation at 0
@@ -131,11 +149,6 @@ __device__ __forceinline__ void renormalize(uint32_t (&M)[64]) {
 #pragma unroll
     // relu(max(M + neg, neg)) == max(M - 63*16, 0): the .relu form needs no zero operand
     for (int s = 0; s < 64; s++) M[s] = __viaddmax_s16x2_relu(M[s], neg, neg);
-}
-
-__device__ __forceinline__ uint32_t pick(const uint4& w, uint32_t q) {
-    const uint32_t lo = (q & 1u) ? w.y : w.x, hi = (q & 1u) ? w.w : w.z;
-    return (q & 2u) ? hi : lo;
 }
 
 // ChainBack (deconvolve.cpp:416-435) for the two frames of this thread.  `es` mirrors the
@@ -150,12 +163,12 @@ __device__ __forceinline__ void trace_step(TraceState& st, const uint4& w, int t
                                            bool liveA, bool liveB) {
     {
         const uint32_t s = st.esA >> 2;  // state of frame A
-        const uint32_t k = (pick(w, s >> 4) >> (((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
+        const uint32_t k = (((s & 32u) ? w.y : w.x) >> (s & 31u)) & 1u;
         st.esA = (st.esA >> 1) | (k << 7);
     }
     {
         const uint32_t s = st.esB >> 2;
-        const uint32_t k = (pick(w, s >> 4) >> (16u + ((s & 1u) << 3) + ((s >> 1) & 7u))) & 1u;
+        const uint32_t k = (((s & 32u) ? w.w : w.z) >> (s & 31u)) & 1u;
         st.esB = (st.esB >> 1) | (k << 7);
     }
     if ((t & 7) == 0) {
@@ -222,7 +235,7 @@ __device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_
 template <bool kWordStores>
 __global__ void __launch_bounds__(kVitThreads, kVitMinBlocks)
 viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
-                    unsigned long long nframes, uint32_t framebits) {
+                    unsigned long long nframes, uint32_t framebits, uint32_t one) {
     const uint32_t steps = framebits + 6;  // framebits is even: 2 * ((F + 6) / 2) == F + 6
     const size_t rowbytes = (size_t)4 * steps, outbytes = (framebits + 7) / 8;
     const uint32_t lane = threadIdx.x & 31u;
@@ -259,22 +272,22 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
                 na0 = __ldg(rowA + q), na1 = __ldg(rowA + q + 1), na2 = __ldg(rowA + q + 2);
                 nb0 = __ldg(rowB + q), nb1 = __ldg(rowB + q + 1), nb2 = __ldg(rowB + q + 2);
             }
-            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x);
-            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y);
+            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x, one);
+            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y, one);
             renormalize(X);
-            dec[(size_t)(t + 2) * 32] = acs_step(X, Y, a1.x, b1.x);
-            dec[(size_t)(t + 3) * 32] = acs_step(Y, X, a1.y, b1.y);
+            dec[(size_t)(t + 2) * 32] = acs_step(X, Y, a1.x, b1.x, one);
+            dec[(size_t)(t + 3) * 32] = acs_step(Y, X, a1.y, b1.y, one);
             renormalize(X);
-            dec[(size_t)(t + 4) * 32] = acs_step(X, Y, a2.x, b2.x);
-            dec[(size_t)(t + 5) * 32] = acs_step(Y, X, a2.y, b2.y);
+            dec[(size_t)(t + 4) * 32] = acs_step(X, Y, a2.x, b2.x, one);
+            dec[(size_t)(t + 5) * 32] = acs_step(Y, X, a2.y, b2.y, one);
             renormalize(X);
             a0 = na0, a1 = na1, a2 = na2, b0 = nb0, b1 = nb1, b2 = nb2;
         }
         for (; t + 2 <= steps; t += 2) {  // framebits not a multiple of 6
             const uint2 a0 = __ldg(rowA + (t >> 1));
             const uint2 b0 = __ldg(rowB + (t >> 1));
-            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x);
-            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y);
+            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x, one);
+            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y, one);
             renormalize(X);
         }
         traceback<kWordStores>(dec, framebits, out + fA * outbytes, out + fB * outbytes, liveA, liveB);
@@ -311,10 +324,10 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
     if (e != cudaSuccess) return e;
     if (framebits % 32 == 0)
         viterbi_pair_kernel<true><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                            framebits);
+                                                                            framebits, 1u);
     else
         viterbi_pair_kernel<false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                             framebits);
+                                                                             framebits, 1u);
     count_launch();
     return cudaGetLastError();
 }
