@@ -61,7 +61,8 @@ LIB_PATH = _build.LIB
 
 
 def _load() -> ctypes.CDLL:
-    path = _build.build_library()  # rebuilds only when sources are newer; raises without nvcc
+    # VITERBI_B200_LIB: developer override to load an alternative build of the same C ABI
+    path = os.environ.get("VITERBI_B200_LIB") or _build.build_library()  # rebuilds only when stale; raises without nvcc
     lib = ctypes.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync

@@ -10,7 +10,10 @@ namespace fec {
 // Viterbi throughput kernel launch shape: one warp per block (64 frames in flight per block),
 // up to kVitMinBlocks resident blocks per SM (register-limited: 2 warps per SM sub-partition x 255 registers).
 constexpr int kVitThreads = 32;
-constexpr int kVitMinBlocks = 8;
+#ifndef VIT_MIN_BLOCKS
+#define VIT_MIN_BLOCKS 8
+#endif
+constexpr int kVitMinBlocks = VIT_MIN_BLOCKS;
 constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision area 256-byte aligned
 
 constexpr int kRsThreads = 128;

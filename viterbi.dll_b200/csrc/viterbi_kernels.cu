@@ -260,6 +260,10 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
         // 6 steps per iteration: after six steps the butterfly renaming of the 64 metric registers
         // returns to the identity, so the loop carries no register moves.  The 48 symbol bytes of the
         // next iteration are fetched while this one computes.
+#ifndef VIT_BODY_STEPS
+#define VIT_BODY_STEPS 2
+#endif
+#if VIT_BODY_STEPS == 6
         uint2 a0, a1, a2, b0, b1, b2;
         if (steps >= 6) {
             a0 = __ldg(rowA), a1 = __ldg(rowA + 1), a2 = __ldg(rowA + 2);
@@ -283,6 +287,20 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
             renormalize(X);
             a0 = na0, a1 = na1, a2 = na2, b0 = nb0, b1 = nb1, b2 = nb2;
         }
+#else
+        {   // 2-step body: smaller instruction footprint, register rotation through moves
+            uint2 a0, b0;
+            if (steps >= 2) a0 = __ldg(rowA), b0 = __ldg(rowB);
+            for (; t + 2 <= steps; t += 2) {
+                uint2 na0 = a0, nb0 = b0;
+                if (t + 4 <= steps) na0 = __ldg(rowA + (t >> 1) + 1), nb0 = __ldg(rowB + (t >> 1) + 1);
+                dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x, one);
+                dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y, one);
+                renormalize(X);
+                a0 = na0, b0 = nb0;
+            }
+        }
+#endif
         for (; t + 2 <= steps; t += 2) {  // framebits not a multiple of 6
             const uint2 a0 = __ldg(rowA + (t >> 1));
             const uint2 b0 = __ldg(rowB + (t >> 1));
