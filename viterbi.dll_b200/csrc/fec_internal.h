@@ -11,7 +11,7 @@ namespace fec {
 // up to kVitMinBlocks resident blocks per SM (register-limited: 2 warps per SM sub-partition x 255 registers).
 constexpr int kVitThreads = 32;
 #ifndef VIT_MIN_BLOCKS
-#define VIT_MIN_BLOCKS 8
+#define VIT_MIN_BLOCKS 12
 #endif
 constexpr int kVitMinBlocks = VIT_MIN_BLOCKS;
 constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision area 256-byte aligned

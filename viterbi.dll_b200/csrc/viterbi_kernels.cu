@@ -107,48 +107,74 @@ __device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_
     }
 }
 
+// Renormalize256 (deconvolve.cpp:407-412): after every second step, if metric[state 0] > 150, 63 is
+// subtracted with saturation at 0 from all 64 metrics -- decided per frame, i.e. per 16-bit half.
+// Returns the per-half addend: -1008 (= -63 * 16) where the frame renormalises, else 0.
+__device__ __forceinline__ uint32_t renorm_addend(uint32_t m0) {
+    // bit 15 of (m0 + 0x7FFF - 2400) is set iff m0 > 2400 (= 150 * 16)
+    const uint32_t hit = ((m0 + 0x769F769Fu) >> 15) & 0x00010001u;
+    return hit * 0xFC10u;
+}
+
 // One trellis step for two frames: old metrics M -> new metrics N, 4 decision words.
 // Per butterfly i (old states i, i+32 -> new states 2i, 2i+1), with m = bm[pattern(i)]:
 //   t1 = min(M[i+32] + (63-m), 255)        candidate through the upper branch, saturated
 //   N[2i] = min(t1, M[i] + m)               == min(sat(M[i]+m), sat(M[i+32]+63-m)) because t1 <= 255
 //   decision(2i) = (t1 <= M[i] + m)         == (N[2i] == t1): ties choose predecessor i+32
 // and symmetrically for 2i+1 (deconvolve.cpp:352-359).
+// kRenorm: the renormalisation that the reference applies after the previous (odd) step is folded
+// into the operand fetch of this step: M' = relu(M + neg), relu(max(M + neg, neg)) == max(M-63*16, 0).
 // Decision words (the reference's decision_t layout, viterbi.h:90-92): x,y = frame A bits 0-31,
 // 32-63; z,w = frame B; bit s = decision of new state s.
+//
+// The file is compiled with ptxas -O1, which keeps this source order, so the loop is software
+// pipelined by hand: the add / add-min stage of butterfly i+1 (2 ALU + 2 FMA-pipe instructions) is
+// issued between the two select stages of butterfly i (2 ALU + 4 FMA-pipe), which keeps both pipes
+// fed and puts 4+ independent instructions between every producer and its consumer.
+template <bool kRenorm>
 __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)[64], uint32_t wA, uint32_t wB,
-                                          uint32_t one) {
+                                          uint32_t one, uint32_t neg) {
+    constexpr int kPat[32] = {pattern(0),  pattern(1),  pattern(2),  pattern(3),  pattern(4),  pattern(5),  pattern(6),
+                              pattern(7),  pattern(8),  pattern(9),  pattern(10), pattern(11), pattern(12), pattern(13),
+                              pattern(14), pattern(15), pattern(16), pattern(17), pattern(18), pattern(19), pattern(20),
+                              pattern(21), pattern(22), pattern(23), pattern(24), pattern(25), pattern(26), pattern(27),
+                              pattern(28), pattern(29), pattern(30), pattern(31)};
     uint32_t bm[8], bmm[8];
     branch_metrics(wA, wB, bm, bmm, one);
     uint32_t dA[2] = {0u, 0u}, dB[2] = {0u, 0u};
+    uint32_t t1[2], t3[2], m0[2], m2[2];
+    {
+        uint32_t a = M[0], b = M[32];
+        if (kRenorm) {
+            a = __viaddmax_s16x2_relu(a, neg, neg);
+            b = __viaddmax_s16x2_relu(b, neg, neg);
+        }
+        t1[0] = __viaddmin_u16x2(b, bmm[kPat[0]], kSat);
+        m0[0] = fma_add(a, bm[kPat[0]], one);
+        t3[0] = __viaddmin_u16x2(b, bm[kPat[0]], kSat);
+        m2[0] = fma_add(a, bmm[kPat[0]], one);
+    }
 #pragma unroll
     for (int i = 0; i < 32; i++) {
-        constexpr int kPat[32] = {pattern(0),  pattern(1),  pattern(2),  pattern(3),  pattern(4),  pattern(5),  pattern(6),
-                                  pattern(7),  pattern(8),  pattern(9),  pattern(10), pattern(11), pattern(12), pattern(13),
-                                  pattern(14), pattern(15), pattern(16), pattern(17), pattern(18), pattern(19), pattern(20),
-                                  pattern(21), pattern(22), pattern(23), pattern(24), pattern(25), pattern(26), pattern(27),
-                                  pattern(28), pattern(29), pattern(30), pattern(31)};
-        const uint32_t m = bm[kPat[i]], mm = bmm[kPat[i]];
-        const uint32_t a = M[i], b = M[i + 32];
-        const uint32_t t1 = __viaddmin_u16x2(b, mm, kSat);
-        const uint32_t t3 = __viaddmin_u16x2(b, m, kSat);
-        const uint32_t m0 = fma_add(a, m, one);
-        const uint32_t m2 = fma_add(a, mm, one);
-        const int w = i >> 4;  // new states 2i, 2i+1 live in decision word (2i) / 32
-        N[2 * i] = min_decide(t1, m0, dA[w], dB[w], one, 1u << ((2 * i) & 31));
-        N[2 * i + 1] = min_decide(t3, m2, dA[w], dB[w], one, 1u << ((2 * i + 1) & 31));
+        const int c = i & 1, n = c ^ 1, w = i >> 4;  // new states 2i, 2i+1 live in decision word (2i) / 32
+        uint32_t a = 0, b = 0;
+        if (i + 1 < 32) {
+            a = M[i + 1], b = M[i + 33];
+            if (kRenorm) a = __viaddmax_s16x2_relu(a, neg, neg);
+        }
+        N[2 * i] = min_decide(t1[c], m0[c], dA[w], dB[w], one, 1u << ((2 * i) & 31));
+        if (i + 1 < 32) {
+            if (kRenorm) b = __viaddmax_s16x2_relu(b, neg, neg);
+            t1[n] = __viaddmin_u16x2(b, bmm[kPat[(i + 1) & 31]], kSat);
+            m0[n] = fma_add(a, bm[kPat[(i + 1) & 31]], one);
+        }
+        N[2 * i + 1] = min_decide(t3[c], m2[c], dA[w], dB[w], one, 1u << ((2 * i + 1) & 31));
+        if (i + 1 < 32) {
+            t3[n] = __viaddmin_u16x2(b, bm[kPat[(i + 1) & 31]], kSat);
+            m2[n] = fma_add(a, bmm[kPat[(i + 1) & 31]], one);
+        }
     }
     return make_uint4(dA[0], dA[1], dB[0], dB[1]);
-}
-
-// Renormalize256 (deconvolve.cpp:407-412): if metric[state 0] > 150 subtract 63 with saturation at 0
-// from all 64 metrics -- decided per frame, i.e. per 16-bit half.
-__device__ __forceinline__ void renormalize(uint32_t (&M)[64]) {
-    // bit 15 of (M0 + 0x7FFF - 2400) is set iff M0 > 2400 (= 150 * 16)
-    const uint32_t hit = ((M[0] + 0x769F769Fu) >> 15) & 0x00010001u;
-    const uint32_t neg = hit * 0xFC10u;  // -1008 (= -63 * 16) in the halves that renormalise, else 0
-#pragma unroll
-    // relu(max(M + neg, neg)) == max(M - 63*16, 0): the .relu form needs no zero operand
-    for (int s = 0; s < 64; s++) M[s] = __viaddmax_s16x2_relu(M[s], neg, neg);
 }
 
 // ChainBack (deconvolve.cpp:416-435) for the two frames of this thread.  `es` mirrors the
@@ -186,7 +212,7 @@ __device__ __forceinline__ void trace_step(TraceState& st, const uint4& w, int t
     }
 }
 
-constexpr int kTraceChunk = 16;  // decision words prefetched per chunk (2 chunks in flight)
+constexpr int kTraceChunk = 8;   // decision words prefetched per chunk (2 chunks in flight)
 
 __device__ __forceinline__ void trace_load(uint4 (&buf)[kTraceChunk], const uint4* __restrict__ dec, int tb) {
 #pragma unroll
@@ -256,57 +282,21 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
 #pragma unroll
         for (int s = 1; s < 64; s++) X[s] = kM63;
 
-        uint32_t t = 0;
-        // 6 steps per iteration: after six steps the butterfly renaming of the 64 metric registers
-        // returns to the identity, so the loop carries no register moves.  The 48 symbol bytes of the
-        // next iteration are fetched while this one computes.
-#ifndef VIT_BODY_STEPS
-#define VIT_BODY_STEPS 2
-#endif
-#if VIT_BODY_STEPS == 6
-        uint2 a0, a1, a2, b0, b1, b2;
-        if (steps >= 6) {
-            a0 = __ldg(rowA), a1 = __ldg(rowA + 1), a2 = __ldg(rowA + 2);
-            b0 = __ldg(rowB), b1 = __ldg(rowB + 1), b2 = __ldg(rowB + 2);
-        }
-        for (; t + 6 <= steps; t += 6) {
-            uint2 na0 = a0, na1 = a1, na2 = a2, nb0 = b0, nb1 = b1, nb2 = b2;
-            if (t + 12 <= steps) {
-                const uint32_t q = (t >> 1) + 3;
-                na0 = __ldg(rowA + q), na1 = __ldg(rowA + q + 1), na2 = __ldg(rowA + q + 2);
-                nb0 = __ldg(rowB + q), nb1 = __ldg(rowB + q + 1), nb2 = __ldg(rowB + q + 2);
-            }
-            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x, one);
-            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y, one);
-            renormalize(X);
-            dec[(size_t)(t + 2) * 32] = acs_step(X, Y, a1.x, b1.x, one);
-            dec[(size_t)(t + 3) * 32] = acs_step(Y, X, a1.y, b1.y, one);
-            renormalize(X);
-            dec[(size_t)(t + 4) * 32] = acs_step(X, Y, a2.x, b2.x, one);
-            dec[(size_t)(t + 5) * 32] = acs_step(Y, X, a2.y, b2.y, one);
-            renormalize(X);
-            a0 = na0, a1 = na1, a2 = na2, b0 = nb0, b1 = nb1, b2 = nb2;
-        }
-#else
-        {   // 2-step body: smaller instruction footprint, register rotation through moves
-            uint2 a0, b0;
-            if (steps >= 2) a0 = __ldg(rowA), b0 = __ldg(rowB);
-            for (; t + 2 <= steps; t += 2) {
-                uint2 na0 = a0, nb0 = b0;
-                if (t + 4 <= steps) na0 = __ldg(rowA + (t >> 1) + 1), nb0 = __ldg(rowB + (t >> 1) + 1);
-                dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x, one);
-                dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y, one);
-                renormalize(X);
-                a0 = na0, b0 = nb0;
-            }
-        }
-#endif
-        for (; t + 2 <= steps; t += 2) {  // framebits not a multiple of 6
-            const uint2 a0 = __ldg(rowA + (t >> 1));
-            const uint2 b0 = __ldg(rowB + (t >> 1));
-            dec[(size_t)(t + 0) * 32] = acs_step(X, Y, a0.x, b0.x, one);
-            dec[(size_t)(t + 1) * 32] = acs_step(Y, X, a0.y, b0.y, one);
-            renormalize(X);
+        // Two steps per iteration (the reference's Butterfly256 granularity): even step X -> Y with the
+        // pending renormalisation folded in, odd step Y -> X, then the renormalisation test on the new
+        // metric of state 0.  The 8 symbol bytes of the next iteration are fetched while this one runs.
+        // (A 6-step body would make the register renaming of the butterfly network close on itself
+        // and save ~30 moves per step, but it overflows the instruction cache once warps are in
+        // different phases: measured 94 vs 118 Gbit/s on the MSC batch.)
+        uint32_t neg = 0u;
+        uint2 a0 = __ldg(rowA), b0 = __ldg(rowB);  // steps >= 6: the first pair always exists
+        for (uint32_t t = 0; t < steps; t += 2) {
+            uint2 na0 = a0, nb0 = b0;
+            if (t + 2 < steps) na0 = __ldg(rowA + (t >> 1) + 1), nb0 = __ldg(rowB + (t >> 1) + 1);
+            dec[(size_t)(t + 0) * 32] = acs_step<true>(X, Y, a0.x, b0.x, one, neg);
+            dec[(size_t)(t + 1) * 32] = acs_step<false>(Y, X, a0.y, b0.y, one, 0u);
+            neg = renorm_addend(X[0]);
+            a0 = na0, b0 = nb0;
         }
         traceback<kWordStores>(dec, framebits, out + fA * outbytes, out + fB * outbytes, liveA, liveB);
 
