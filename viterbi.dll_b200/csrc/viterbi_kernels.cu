@@ -177,46 +177,48 @@ __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)
     return make_uint4(dA[0], dA[1], dB[0], dB[1]);
 }
 
-// ChainBack (deconvolve.cpp:416-435) for the two frames of this thread.  `es` mirrors the
-// reference's 8-bit EndState register (state << 2); the decoded byte is final when t % 8 == 0
-// (the reference stores on every step, the last store wins).
+// ChainBack (deconvolve.cpp:416-435) for the two frames of this thread.
+// The reference keeps state << 2 in an 8-bit register and shifts each decision in at bit 7.  Here
+// the same register is 32 bits wide: h = (h >> 1) | (k << 31), so the state is h >> 26, the
+// reference's byte is h >> 24, and after 32 steps h holds 32 decoded bits (bit 31 = earliest).
+// Per step and frame: pick the decision word by state bit 5 (the sign of h), funnel-shift it by the
+// low 5 state bits, funnel-shift its bit 0 into h -- a 4-instruction dependent chain.
 struct TraceState {
-    uint32_t esA = 0, esB = 0, wordA = 0, wordB = 0;
+    uint32_t hA = 0, hB = 0;
 };
 
 template <bool kWordStores>
 __device__ __forceinline__ void trace_step(TraceState& st, const uint4& w, int t, uint8_t* outA, uint8_t* outB,
                                            bool liveA, bool liveB) {
-    {
-        const uint32_t s = st.esA >> 2;  // state of frame A
-        const uint32_t k = (((s & 32u) ? w.y : w.x) >> (s & 31u)) & 1u;
-        st.esA = (st.esA >> 1) | (k << 7);
-    }
-    {
-        const uint32_t s = st.esB >> 2;
-        const uint32_t k = (((s & 32u) ? w.w : w.z) >> (s & 31u)) & 1u;
-        st.esB = (st.esB >> 1) | (k << 7);
-    }
-    if ((t & 7) == 0) {
-        if (kWordStores) {
-            st.wordA = (st.wordA << 8) | st.esA;
-            st.wordB = (st.wordB << 8) | st.esB;
-            if ((t & 31) == 0) {
-                if (liveA) *reinterpret_cast<uint32_t*>(outA + (t >> 3)) = st.wordA;
-                if (liveB) *reinterpret_cast<uint32_t*>(outB + (t >> 3)) = st.wordB;
-            }
-        } else {
-            if (liveA) outA[t >> 3] = (uint8_t)st.esA;
-            if (liveB) outB[t >> 3] = (uint8_t)st.esB;
+    const uint32_t xA = __funnelshift_r((int32_t)st.hA < 0 ? w.y : w.x, 0u, st.hA >> 26);
+    const uint32_t xB = __funnelshift_r((int32_t)st.hB < 0 ? w.w : w.z, 0u, st.hB >> 26);
+    st.hA = __funnelshift_r(st.hA, xA, 1);
+    st.hB = __funnelshift_r(st.hB, xB, 1);
+    if (kWordStores) {
+        if ((t & 31) == 0) {  // bytes t/8 .. t/8+3, MSB-first within each byte
+            if (liveA) *reinterpret_cast<uint32_t*>(outA + (t >> 3)) = __byte_perm(st.hA, 0u, 0x0123);
+            if (liveB) *reinterpret_cast<uint32_t*>(outB + (t >> 3)) = __byte_perm(st.hB, 0u, 0x0123);
         }
+    } else if ((t & 7) == 0) {  // the reference stores every step; the store at t % 8 == 0 is the final one
+        if (liveA) outA[t >> 3] = (uint8_t)(st.hA >> 24);
+        if (liveB) outB[t >> 3] = (uint8_t)(st.hB >> 24);
     }
 }
 
-constexpr int kTraceChunk = 8;   // decision words prefetched per chunk (2 chunks in flight)
+constexpr int kTraceChunk = 12;      // decision words per register buffer (2 buffers in flight)
+constexpr int kTracePrefetch = 96;   // steps ahead that are pulled into L2
 
 __device__ __forceinline__ void trace_load(uint4 (&buf)[kTraceChunk], const uint4* __restrict__ dec, int tb) {
 #pragma unroll
     for (int j = 0; j < kTraceChunk; j++) buf[j] = dec[(size_t)(tb + j + 6) * 32];
+}
+
+// Each lane prefetches its own 16 bytes; the 32 lanes together touch the 4 lines of one step.
+__device__ __forceinline__ void trace_prefetch_l2(const uint4* __restrict__ dec, int tb) {
+    if (tb < 0) return;
+#pragma unroll
+    for (int j = 0; j < kTraceChunk; j++)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dec + (size_t)(tb + j + 6) * 32));
 }
 
 template <bool kWordStores>
@@ -226,25 +228,30 @@ __device__ __forceinline__ void trace_chunk(TraceState& st, const uint4 (&buf)[k
     for (int j = kTraceChunk - 1; j >= 0; j--) trace_step<kWordStores>(st, buf[j], tb + j, outA, outB, liveA, liveB);
 }
 
-// The state recursion is serial, but the decision words it consumes do not depend on it: they are
-// fetched a chunk ahead (double-buffered in the registers the path metrics no longer need), so the
-// traceback runs at ALU latency instead of one global-memory round trip per step.
+// The state recursion is serial, but the decision words it consumes do not depend on it.  They were
+// written by this same thread and have mostly been evicted to HBM by now, so they are pulled back in
+// two stages: an L2 prefetch kTracePrefetch steps ahead, and register double-buffering one chunk
+// ahead (in the registers the path metrics no longer need).  The traceback then runs at ALU latency
+// instead of one memory round trip per chunk.
 template <bool kWordStores>
 __device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_t framebits, uint8_t* outA,
                                           uint8_t* outB, bool liveA, bool liveB) {
     TraceState st;
     int t = (int)framebits - 1;
     const int head = (int)(framebits % kTraceChunk);
+    int tb = t - head + 1 - kTraceChunk;  // base of the first full chunk (a multiple of kTraceChunk)
+    for (int d = 0; d < kTracePrefetch; d += kTraceChunk) trace_prefetch_l2(dec, tb - d);
     for (int i = 0; i < head; i++, t--) trace_step<kWordStores>(st, dec[(size_t)(t + 6) * 32], t, outA, outB, liveA, liveB);
-    int tb = t + 1 - kTraceChunk;  // base of the next full chunk (a multiple of kTraceChunk)
     if (tb < 0) return;
     uint4 bufA[kTraceChunk], bufB[kTraceChunk];
     trace_load(bufA, dec, tb);
     while (true) {
+        trace_prefetch_l2(dec, tb - kTracePrefetch);
         if (tb >= kTraceChunk) trace_load(bufB, dec, tb - kTraceChunk);
         trace_chunk<kWordStores>(st, bufA, tb, outA, outB, liveA, liveB);
         tb -= kTraceChunk;
         if (tb < 0) break;
+        trace_prefetch_l2(dec, tb - kTracePrefetch);
         if (tb >= kTraceChunk) trace_load(bufA, dec, tb - kTraceChunk);
         trace_chunk<kWordStores>(st, bufB, tb, outA, outB, liveA, liveB);
         tb -= kTraceChunk;
