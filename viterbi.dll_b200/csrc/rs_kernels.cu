@@ -33,6 +33,7 @@ struct RsTables {
     uint8_t ato[768];   // alpha^(i mod 255), dllmain.cpp:145-146
     uint8_t iof[256];   // log, log(0) = 255, dllmain.cpp:131-143
     uint4 lfsr[256];    // c * (g(x) - x^10): coefficients x^0..x^9 in bytes 0..9
+    uint8_t mulpow[NROOTS][256];  // mulpow[j-1][v] = v * alpha^j: one Chien step of the x^j term
 };
 
 __constant__ RsTables c_tables;
@@ -40,11 +41,40 @@ __constant__ RsTables c_tables;
 // rschecksf.cpp:50-52
 __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u) >> 24; }
 
+// Chien search (rschecksf.cpp:296-320) for a locator of degree D: evaluate lambda at alpha^i for
+// i = 1..255 and record the roots, stopping once D roots are found.  The reference keeps the terms
+// in index form and adds j to the exponent of the x^j term every iteration; here the terms stay in
+// polynomial form and are multiplied by alpha^j through a 256-byte table -- the same field
+// elements, one shared-memory lookup per term and position instead of add + mod + lookup.
+template <int D>
+__device__ __forceinline__ int chien(const uint8_t (&lam_poly)[NROOTS + 1], const uint8_t* __restrict__ mulpow,
+                                     uint8_t (&root)[NROOTS + 1]) {
+    uint32_t term[D > 0 ? D : 1];
+#pragma unroll
+    for (int j = 0; j < D; j++) term[j] = lam_poly[j + 1];
+    int count = 0;
+    for (int i = 1; i <= NN; i++) {
+        uint32_t q = 1;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            term[j] = mulpow[j * 256 + term[j]];
+            q ^= term[j];
+        }
+        if (q != 0) continue;
+#pragma unroll
+        for (int c = 0; c < NROOTS; c++)
+            if (c == count) root[c] = (uint8_t)i;
+        if (++count == D) break;
+    }
+    return count;
+}
+
 // Decode one codeword stored at col[k * stride], k = 0..119, in place.  Returns the number of
 // roots found (= corrected symbols as the reference counts them), 0 for a clean word, -1 if
 // uncorrectable.
 __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __restrict__ ato,
-                                const uint8_t* __restrict__ iof, const uint4* __restrict__ lfsr) {
+                                const uint8_t* __restrict__ iof, const uint4* __restrict__ lfsr,
+                                const uint8_t* __restrict__ mulpow) {
     // ---- remainder of cw(x) mod g(x); cw[0] is the highest-degree coefficient -----------------
     uint32_t r0 = 0, r1 = 0, r2 = 0;  // coefficients x^0..x^3 | x^4..x^7 | x^8,x^9
 #pragma unroll 4
@@ -120,32 +150,30 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
         }
     }
 
+    uint8_t lam_poly[NROOTS + 1];
     int deg_lambda = 0;
 #pragma unroll
     for (int i = 0; i <= NROOTS; i++) {
+        lam_poly[i] = lam[i];
         lam[i] = iof[lam[i]];
         if (lam[i] != NN) deg_lambda = i;
     }
 
-    // ---- Chien search (rschecksf.cpp:296-320) ---------------------------------------------------
-    uint32_t e[NROOTS + 1];
-#pragma unroll
-    for (int j = 1; j <= NROOTS; j++) e[j] = lam[j];
+    // ---- Chien search, specialised by degree ------------------------------------------------------
     uint8_t root[NROOTS + 1];
     int count = 0;
-    for (int i = 1; i <= NN; i++) {
-        uint32_t q = 1;
-#pragma unroll
-        for (int j = NROOTS; j > 0; j--)
-            if (j <= deg_lambda && e[j] != NN) {
-                e[j] = mod255(e[j] + j);
-                q ^= ato[e[j]];
-            }
-        if (q != 0) continue;
-#pragma unroll
-        for (int c = 0; c < NROOTS; c++)
-            if (c == count) root[c] = (uint8_t)i;
-        if (++count == deg_lambda) break;
+    switch (deg_lambda) {
+        case 1: count = chien<1>(lam_poly, mulpow, root); break;
+        case 2: count = chien<2>(lam_poly, mulpow, root); break;
+        case 3: count = chien<3>(lam_poly, mulpow, root); break;
+        case 4: count = chien<4>(lam_poly, mulpow, root); break;
+        case 5: count = chien<5>(lam_poly, mulpow, root); break;
+        case 6: count = chien<6>(lam_poly, mulpow, root); break;
+        case 7: count = chien<7>(lam_poly, mulpow, root); break;
+        case 8: count = chien<8>(lam_poly, mulpow, root); break;
+        case 9: count = chien<9>(lam_poly, mulpow, root); break;
+        case 10: count = chien<10>(lam_poly, mulpow, root); break;
+        default: break;  // degree 0: no roots to find, count == deg_lambda == 0
     }
     if (deg_lambda != count) return -1;  // rschecksf.cpp:325-326
 
@@ -187,7 +215,7 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
 }  // namespace
 
 // One block = `sf_per_block` whole superframes; dynamic shared memory:
-//   [tables: ato 768 | iof 256 | lfsr 4096] [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
+//   [tables: lfsr 4096 | ato 768 | iof 256 | mulpow 2560] [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
 __global__ void __launch_bounds__(kRsThreads)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
                      unsigned long long nsf, uint32_t s, uint32_t sf_per_block) {
@@ -195,7 +223,8 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     uint4* s_lfsr = reinterpret_cast<uint4*>(smem);
     uint8_t* s_ato = smem + 4096;
     uint8_t* s_iof = s_ato + 768;
-    int* s_fail = reinterpret_cast<int*>(s_iof + 256);
+    uint8_t* s_mulpow = s_iof + 256;
+    int* s_fail = reinterpret_cast<int*>(s_mulpow + NROOTS * 256);
     int* s_sum = s_fail + sf_per_block;
     uint8_t* tile = reinterpret_cast<uint8_t*>(s_sum + sf_per_block);
     tile += (16 - (reinterpret_cast<uintptr_t>(tile) & 15)) & 15;
@@ -204,6 +233,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     for (uint32_t i = tid; i < 256; i += blockDim.x) s_lfsr[i] = c_tables.lfsr[i];
     for (uint32_t i = tid; i < 768; i += blockDim.x) s_ato[i] = c_tables.ato[i];
     for (uint32_t i = tid; i < 256; i += blockDim.x) s_iof[i] = c_tables.iof[i];
+    for (uint32_t i = tid; i < NROOTS * 256; i += blockDim.x) s_mulpow[i] = c_tables.mulpow[i >> 8][i & 255];
 
     const size_t sf_in = (size_t)CW * s, sf_out = (size_t)DATA * s;
     const unsigned long long nblk = (nsf + sf_per_block - 1) / sf_per_block;
@@ -230,7 +260,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
         const uint32_t ncw = nloc * s;
         for (uint32_t c = tid; c < ncw; c += blockDim.x) {
             const uint32_t n = c / s, j = c - n * s;
-            const int r = rs_decode_column(tile + n * sf_in + j, s, s_ato, s_iof, s_lfsr);
+            const int r = rs_decode_column(tile + n * sf_in + j, s, s_ato, s_iof, s_lfsr, s_mulpow);
             if (r < 0)
                 atomicMin(&s_fail[n], (int)j);
             else if (r > 0)
@@ -268,7 +298,8 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
 
 size_t rs_smem_bytes(uint32_t s, uint32_t sf_per_block) {
     // + 16 alignment slack + 8 so the word gather may read one aligned word past the tile
-    return 4096 + 768 + 256 + 2 * sizeof(int) * (size_t)sf_per_block + 16 + (size_t)CW * s * sf_per_block + 8;
+    return 4096 + 768 + 256 + NROOTS * 256 + 2 * sizeof(int) * (size_t)sf_per_block + 16 +
+           (size_t)CW * s * sf_per_block + 8;
 }
 
 uint32_t rs_superframes_per_block(uint32_t s) {
@@ -311,6 +342,8 @@ cudaError_t rs_upload_tables() {
             w[q] = row[4 * q] | (row[4 * q + 1] << 8) | (row[4 * q + 2] << 16) | ((uint32_t)row[4 * q + 3] << 24);
         h.lfsr[c] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    for (int j = 1; j <= NROOTS; j++)
+        for (unsigned v = 0; v < 256; v++) h.mulpow[j - 1][v] = mul((uint8_t)v, alpha[j]);
     return cudaMemcpyToSymbol(c_tables, &h, sizeof(h));
 }
 
