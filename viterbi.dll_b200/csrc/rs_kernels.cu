@@ -41,15 +41,19 @@ __constant__ RsTables c_tables;
 // rschecksf.cpp:50-52
 __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u) >> 24; }
 
-// Chien search (rschecksf.cpp:296-320) for a locator of degree D: evaluate lambda at alpha^i for
-// i = 1..255 and record the roots, stopping once D roots are found.  The reference keeps the terms
-// in index form and adds j to the exponent of the x^j term every iteration; here the terms stay in
-// polynomial form and are multiplied by alpha^j through a 256-byte table -- the same field
-// elements, one shared-memory lookup per term and position instead of add + mod + lookup.
+// Chien search (rschecksf.cpp:296-320): evaluate lambda at alpha^i for i = 1..255 and record the
+// roots, stopping once deg(lambda) roots are found.  The reference keeps the terms in index form and
+// adds j to the exponent of the x^j term every iteration; here the terms stay in polynomial form and
+// are multiplied by alpha^j through a 256-byte table -- the same field elements, one shared-memory
+// lookup per term and position instead of add + mod + lookup.
+// D is the largest degree in the warp (warp-uniform, so the warp runs ONE instantiation instead of
+// serialising one loop per distinct degree); coefficients above a lane's own degree are zero and
+// stay zero under the multiplication.  A degree-d polynomial has at most d roots, so running past a
+// lane's own early-exit point cannot change its count.
 template <int D>
 __device__ __forceinline__ int chien(const uint8_t (&lam_poly)[NROOTS + 1], const uint8_t* __restrict__ mulpow,
-                                     uint8_t (&root)[NROOTS + 1]) {
-    uint32_t term[D > 0 ? D : 1];
+                                     uint8_t (&root)[NROOTS + 1], int deg, unsigned mask) {
+    uint32_t term[D];
 #pragma unroll
     for (int j = 0; j < D; j++) term[j] = lam_poly[j + 1];
     int count = 0;
@@ -60,21 +64,25 @@ __device__ __forceinline__ int chien(const uint8_t (&lam_poly)[NROOTS + 1], cons
             term[j] = mulpow[j * 256 + term[j]];
             q ^= term[j];
         }
-        if (q != 0) continue;
+        if (q == 0 && count < deg) {
 #pragma unroll
-        for (int c = 0; c < NROOTS; c++)
-            if (c == count) root[c] = (uint8_t)i;
-        if (++count == D) break;
+            for (int c = 0; c < NROOTS; c++)
+                if (c == count) root[c] = (uint8_t)i;
+            count++;
+        }
+        if ((i & 7) == 0 && !__any_sync(mask, count < deg)) break;  // every lane has all its roots
     }
     return count;
 }
 
 // Decode one codeword stored at col[k * stride], k = 0..119, in place.  Returns the number of
 // roots found (= corrected symbols as the reference counts them), 0 for a clean word, -1 if
-// uncorrectable.
+// uncorrectable.  Called by all lanes of `mask` together: control flow is kept warp-uniform (clean
+// lanes ride along with all-zero syndromes, which Berlekamp-Massey turns into lambda = 1, degree 0,
+// zero roots, return value 0 -- exactly the reference's early return).
 __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __restrict__ ato,
                                 const uint8_t* __restrict__ iof, const uint4* __restrict__ lfsr,
-                                const uint8_t* __restrict__ mulpow) {
+                                const uint8_t* __restrict__ mulpow, unsigned mask) {
     // ---- remainder of cw(x) mod g(x); cw[0] is the highest-degree coefficient -----------------
     uint32_t r0 = 0, r1 = 0, r2 = 0;  // coefficients x^0..x^3 | x^4..x^7 | x^8,x^9
 #pragma unroll 4
@@ -88,7 +96,8 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
         r1 ^= row.y;
         r2 ^= row.z;
     }
-    if ((r0 | r1 | r2) == 0u) return 0;  // all syndromes zero (rschecksf.cpp:224-230)
+    // all syndromes zero <=> remainder zero (rschecksf.cpp:224-230); skip the rest if the whole warp is clean
+    if (!__any_sync(mask, (r0 | r1 | r2) != 0u)) return 0;
 
     // ---- syndromes S_i = rem(alpha^i), then index form (rschecksf.cpp:232-233) ------------------
     uint8_t syn[NROOTS];
@@ -159,21 +168,21 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
         if (lam[i] != NN) deg_lambda = i;
     }
 
-    // ---- Chien search, specialised by degree ------------------------------------------------------
+    // ---- Chien search, one instantiation per warp (largest degree present) ---------------------------
     uint8_t root[NROOTS + 1];
     int count = 0;
-    switch (deg_lambda) {
-        case 1: count = chien<1>(lam_poly, mulpow, root); break;
-        case 2: count = chien<2>(lam_poly, mulpow, root); break;
-        case 3: count = chien<3>(lam_poly, mulpow, root); break;
-        case 4: count = chien<4>(lam_poly, mulpow, root); break;
-        case 5: count = chien<5>(lam_poly, mulpow, root); break;
-        case 6: count = chien<6>(lam_poly, mulpow, root); break;
-        case 7: count = chien<7>(lam_poly, mulpow, root); break;
-        case 8: count = chien<8>(lam_poly, mulpow, root); break;
-        case 9: count = chien<9>(lam_poly, mulpow, root); break;
-        case 10: count = chien<10>(lam_poly, mulpow, root); break;
-        default: break;  // degree 0: no roots to find, count == deg_lambda == 0
+    switch (__reduce_max_sync(mask, (unsigned)deg_lambda)) {
+        case 1: count = chien<1>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 2: count = chien<2>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 3: count = chien<3>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 4: count = chien<4>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 5: count = chien<5>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 6: count = chien<6>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 7: count = chien<7>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 8: count = chien<8>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 9: count = chien<9>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 10: count = chien<10>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        default: break;  // every lane has degree 0: nothing to search
     }
     if (deg_lambda != count) return -1;  // rschecksf.cpp:325-326
 
@@ -258,13 +267,17 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
         __syncthreads();
         // ---- decode: one thread per codeword, corrections applied in place in the tile ------------
         const uint32_t ncw = nloc * s;
-        for (uint32_t c = tid; c < ncw; c += blockDim.x) {
-            const uint32_t n = c / s, j = c - n * s;
-            const int r = rs_decode_column(tile + n * sf_in + j, s, s_ato, s_iof, s_lfsr, s_mulpow);
-            if (r < 0)
-                atomicMin(&s_fail[n], (int)j);
-            else if (r > 0)
-                atomicAdd(&s_sum[n], r);
+        for (uint32_t c0 = tid & ~31u; c0 < ncw; c0 += blockDim.x) {  // warp-uniform trip count
+            const uint32_t c = c0 + (tid & 31u);
+            const unsigned mask = __ballot_sync(0xffffffffu, c < ncw);
+            if (c < ncw) {
+                const uint32_t n = c / s, j = c - n * s;
+                const int r = rs_decode_column(tile + n * sf_in + j, s, s_ato, s_iof, s_lfsr, s_mulpow, mask);
+                if (r < 0)
+                    atomicMin(&s_fail[n], (int)j);
+                else if (r > 0)
+                    atomicAdd(&s_sum[n], r);
+            }
         }
         __syncthreads();
         // ---- return values: sum of the per-column counts, or -1 (rschecksf.cpp:80-88) -------------
