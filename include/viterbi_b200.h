@@ -111,6 +111,14 @@ int fec_memcpy_h2d(void* d_dst, const void* src, size_t bytes);
 int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
 int fec_device_synchronize(void);
 
+/* Viterbi kernel selection: 0 = automatic (warp-per-frame kernel below 4,096 frames per launch, the
+ * two-frames-per-thread throughput kernel above), 1 = always the throughput kernel, 2 = always the
+ * warp-per-frame kernel.  Both are bit-exact; this exists for tests and measurements. */
+#define FEC_VITERBI_AUTO 0
+#define FEC_VITERBI_PAIR 1
+#define FEC_VITERBI_WARP 2
+int fec_set_viterbi_kernel(int mode);
+
 /* number of kernels this library has launched since load (for benchmark accounting) */
 unsigned long long fec_kernel_launches(void);
 

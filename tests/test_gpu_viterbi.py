@@ -18,10 +18,20 @@ def _device(vb):
     assert vb.lib.fec_device_count() > 0, "no CUDA device: the product has no CPU fallback"
     assert vb.initialize()
     yield
+    vb.set_viterbi_kernel(vb.VITERBI_AUTO)
     assert vb.lib.fec_in_save_mode() == 0
 
 
-def test_known_answers_through_dropin_deconvolve(vb, golden_dir):
+@pytest.fixture(params=["pair", "warp"])
+def kernel(request, vb):
+    """Run the test once per Viterbi kernel: the two-frames-per-thread throughput kernel and the
+    warp-per-frame latency kernel (automatic selection would pick by batch size)."""
+    vb.set_viterbi_kernel(vb.VITERBI_PAIR if request.param == "pair" else vb.VITERBI_WARP)
+    yield request.param
+    vb.set_viterbi_kernel(vb.VITERBI_AUTO)
+
+
+def test_known_answers_through_dropin_deconvolve(vb, kernel, golden_dir):
     kat = json.load(open(os.path.join(golden_dir, "kat.json")))
     for e in kat["viterbi"]:
         if e.get("symbols_hex"):
@@ -33,7 +43,7 @@ def test_known_answers_through_dropin_deconvolve(vb, golden_dir):
         assert hashlib.sha256(out.tobytes()).hexdigest() == e["out_sha256"], e["name"]
 
 
-def test_golden_fixture_host_and_device(vb, golden_dir):
+def test_golden_fixture_host_and_device(vb, kernel, golden_dir):
     import torch
 
     fx = np.load(os.path.join(golden_dir, "viterbi_fixture.npz"))
@@ -51,18 +61,18 @@ def test_golden_fixture_host_and_device(vb, golden_dir):
 @pytest.mark.parametrize("framebits,ebn0,n", [(768, 3.0, 4096), (768, 0.0, 1000), (3072, 0.0, 700), (3072, 3.0, 1500),
                                               (3072, 6.0, 700), (1536, 2.0, 513), (2304, 4.0, 257), (9216, 3.0, 130),
                                               (2, 1.0, 200), (10, 1.0, 65), (100, 2.0, 63), (770, 3.0, 129), (772, 3.0, 64)])
-def test_random_frames_match_checker(vb, checker, framebits, ebn0, n):
+def test_random_frames_match_checker(vb, kernel, checker, framebits, ebn0, n):
     sym, _ = dabgen.make_frames(n, framebits, ebn0, seed=framebits * 7 + n)
     assert np.array_equal(vb.deconvolve_batch(framebits, sym), checker.deconvolve_batch(framebits, sym))
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 1000])
-def test_ragged_batch_sizes(vb, checker, n):
+def test_ragged_batch_sizes(vb, kernel, checker, n):
     sym, _ = dabgen.make_frames(n, 768, 2.0, seed=n)
     assert np.array_equal(vb.deconvolve_batch(768, sym), checker.deconvolve_batch(768, sym))
 
 
-def test_adversarial_symbols(vb, checker):
+def test_adversarial_symbols(vb, kernel, checker):
     rng = np.random.default_rng(11)
     for f in (768, 3072):
         ns = 4 * (f + 6)
@@ -75,7 +85,7 @@ def test_adversarial_symbols(vb, checker):
         assert np.array_equal(vb.deconvolve_batch(f, sym), checker.deconvolve_batch(f, sym)), f
 
 
-def test_out_of_range_symbols_low_byte_only(vb, checker):
+def test_out_of_range_symbols_low_byte_only(vb, kernel, checker):
     """README.md:19 edge case: words above 255 -- only the low byte counts (deconvolve.cpp:219-228)."""
     rng = np.random.default_rng(12)
     sym, _ = dabgen.make_frames(70, 768, 3.0, seed=5)
@@ -91,7 +101,7 @@ def test_empty_and_zero_length(vb):
     assert vb.deconvolve_batch(0, np.zeros((5, 24), np.uint8)).shape == (5, 0)  # F = 0: nothing to write
 
 
-def test_ber_fer_curve_identical_to_checker(vb, checker):
+def test_ber_fer_curve_identical_to_checker(vb, kernel, checker):
     """Eb/N0 sweep 0..6 dB (BASELINE config 3, reduced count): same decoded bits => same BER/FER."""
     for eb in range(0, 7):
         sym, bits = dabgen.make_frames(384, 3072, float(eb), seed=1000 + eb)
@@ -103,6 +113,17 @@ def test_ber_fer_curve_identical_to_checker(vb, checker):
             assert ber > 1e-2
         if eb == 6:
             assert ber < 1e-5 and fer < 0.02
+
+
+def test_automatic_kernel_selection_agrees(vb, checker):
+    """Below 4,096 frames per launch the library picks the warp kernel, above it the pair kernel."""
+    vb.set_viterbi_kernel(vb.VITERBI_AUTO)
+    for n in (100, 4095, 4096, 6000):
+        sym, _ = dabgen.make_frames(n, 96, 2.0, seed=n)
+        l0 = vb.kernel_launches()
+        got = vb.deconvolve_batch(96, sym)
+        assert vb.kernel_launches() > l0
+        assert np.array_equal(got, checker.deconvolve_batch(96, sym)), n
 
 
 def test_full_size_fic_roundtrip_on_device(vb):

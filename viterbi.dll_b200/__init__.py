@@ -54,6 +54,7 @@ _SIGNATURES = {
     "fec_memcpy_h2d": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "fec_memcpy_d2h": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "fec_device_synchronize": (ctypes.c_int, []),
+    "fec_set_viterbi_kernel": (ctypes.c_int, [ctypes.c_int]),
     "fec_kernel_launches": (ctypes.c_ulonglong, []),
 }
 
@@ -180,6 +181,14 @@ def rs_check_superframe_batch_device(rx, RSDims: int, out, ret=None, stream=None
     rc = lib.rs_check_superframe_batch_device(rx.data_ptr(), RSDims, n, out.data_ptr(), ret.data_ptr(), _stream_ptr(stream))
     _check(rc, "rs_check_superframe_batch_device")
     return out, ret
+
+
+VITERBI_AUTO, VITERBI_PAIR, VITERBI_WARP = 0, 1, 2
+
+
+def set_viterbi_kernel(mode: int) -> None:
+    """0 auto, 1 two-frames-per-thread throughput kernel, 2 warp-per-frame kernel (tests / measurements)."""
+    _check(lib.fec_set_viterbi_kernel(mode), "fec_set_viterbi_kernel")
 
 
 def kernel_launches() -> int:

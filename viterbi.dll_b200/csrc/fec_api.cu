@@ -26,6 +26,7 @@ constexpr int kPipe = 3;  // host-path pipeline depth (streams / staging slots)
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_save_mode{0};
 std::atomic<int> g_device{-1};  // -1: use the calling thread's current device
+std::atomic<int> g_vit_kernel{FEC_VITERBI_AUTO};
 thread_local std::string t_error;
 
 struct DeviceState {
@@ -150,6 +151,12 @@ bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= 
 int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
                cudaStream_t stream, void* scratch, size_t scratch_cap) {
     if (n == 0 || framebits == 0) return FEC_OK;
+    const int mode = g_vit_kernel.load();
+    if (mode == FEC_VITERBI_WARP || (mode == FEC_VITERBI_AUTO && n < kVitWarpKernelMaxFrames))
+        // latency / small-batch path: decisions stay in shared memory
+        return fail(launch_viterbi_warp(d_syms, d_out, n, framebits, st->num_sms, stream), "viterbi warp kernel launch")
+                   ? FEC_ERR_DEVICE
+                   : FEC_OK;
     const int blocks = viterbi_grid_blocks(st->num_sms, n);
     const size_t need = viterbi_scratch_bytes(blocks, framebits);
     void* ws = scratch;
@@ -424,6 +431,12 @@ int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes) {
 }
 
 int fec_device_synchronize(void) { return fail(cudaDeviceSynchronize(), "cudaDeviceSynchronize") ? FEC_ERR_DEVICE : FEC_OK; }
+
+int fec_set_viterbi_kernel(int mode) {
+    if (mode < FEC_VITERBI_AUTO || mode > FEC_VITERBI_WARP) return bad_arg("unknown kernel mode");
+    g_vit_kernel.store(mode);
+    return FEC_OK;
+}
 
 unsigned long long fec_kernel_launches(void) { return g_launches.load(); }
 

@@ -16,6 +16,10 @@ constexpr int kVitThreads = 32;
 constexpr int kVitMinBlocks = VIT_MIN_BLOCKS;
 constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision area 256-byte aligned
 
+// Batches below this size go to the warp-per-frame kernel (the pair kernel needs 64 frames per warp
+// and ~600 warps to fill the device).  Measured crossover (profiles/kernel_crossover_r01.jsonl):
+// between 4,096 and 8,192 frames at F=768, between 2,048 and 4,096 at F=3072.
+constexpr unsigned long long kVitWarpKernelMaxFrames = 4096;
 constexpr int kRsThreads = 128;
 
 void count_launch();
@@ -24,6 +28,8 @@ size_t viterbi_scratch_bytes(int grid_blocks, uint32_t framebits);
 int viterbi_grid_blocks(int num_sms, unsigned long long nframes);
 cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_scratch, unsigned long long nframes,
                                 uint32_t framebits, int grid_blocks, cudaStream_t stream);
+cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
+                                int num_sms, cudaStream_t stream);
 cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t nsymbols, int num_sms,
                                    cudaStream_t stream);
 

@@ -313,6 +313,96 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Latency / small-batch kernel: one warp per frame, lane L holds states L and L+32.
+//
+// This is the layout of the design brief: the butterfly L (old states L, L+32 -> new states 2L, 2L+1)
+// needs no communication; the next step then needs new states L and L+32, which lanes L>>1 and
+// 16+(L>>1) hold, so each step exchanges one packed {even, odd} pair through two shuffles.  Soft
+// symbols are staged into shared memory with coalesced 8-byte loads and read back as one broadcast word
+// per step; the 64 decision bits of a step are two warp ballots (even / odd new states) stored in shared
+// memory, and lane 0 runs the traceback out of shared memory -- decisions never leave the SM.
+// It costs ~30 warp-instructions per trellis step (the pair kernel: 416 per 64 frame-steps = 6.5), so
+// it is used where the pair kernel cannot fill the machine: the single-frame drop-in call and batches
+// below kVitWarpKernelMaxFrames.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) viterbi_warp_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
+                                                          unsigned long long nframes, uint32_t framebits) {
+    extern __shared__ __align__(16) uint8_t wsmem[];
+    const uint32_t steps = framebits + 6, lane = threadIdx.x;
+    uint32_t* s_sym = reinterpret_cast<uint32_t*>(wsmem);         // [steps] 4 symbols per step
+    uint2* s_dec = reinterpret_cast<uint2*>(wsmem + 4 * (size_t)steps);  // [steps] {even, odd} ballots
+    const size_t outbytes = (framebits + 7) / 8;
+
+    // branch masks of butterfly `lane` (const.asm:35-49 restated): 0xFF where the expected code bit is 1
+    const uint32_t xmask = (parity8((2u * lane) & kPoly(0)) ? 0xFF0000FFu : 0u) |  // polys 0 and 3 coincide
+                           (parity8((2u * lane) & kPoly(1)) ? 0x0000FF00u : 0u) |
+                           (parity8((2u * lane) & kPoly(2)) ? 0x00FF0000u : 0u);
+    const uint32_t half_sel = (lane & 1u) ? 0x4432u : 0x4410u;  // pick the odd / even half of a packed pair
+    const uint32_t srcA = lane >> 1, srcB = 16u + (lane >> 1);
+
+    for (unsigned long long f = blockIdx.x; f < nframes; f += gridDim.x) {
+        const uint2* row = reinterpret_cast<const uint2*>(syms + f * 4 * (size_t)steps);
+        __syncwarp();
+        for (uint32_t i = lane; i < steps / 2; i += 32) reinterpret_cast<uint2*>(s_sym)[i] = __ldg(row + i);
+        __syncwarp();
+
+        uint32_t A = (lane == 0) ? 0u : 63u, B = 63u;  // Locals256: M[0] = 0, others 63 (deconvolve.cpp:130-132)
+        // branch metric (deconvolve.cpp:338-349): avg(avg(x0,x1), avg(x2,x3)) >> 2, pavgb rounds up.
+        // It does not depend on the path metrics, so the metric of step t+1 is computed while the
+        // shuffles of step t are in flight: the serial chain per step is add-min, add-min, pack,
+        // shuffle, unpack.
+        auto branch_metric = [xmask](uint32_t w) {
+            const uint32_t x = w ^ xmask;
+            const uint32_t s = (x & 0x00FF00FFu) + ((x >> 8) & 0x00FF00FFu) + 0x00010001u;  // x0+x1+1 | x2+x3+1
+            const uint32_t ab = (s >> 1) & 0x00FF00FFu;
+            return ((ab & 0xFFFFu) + (ab >> 16) + 1u) >> 3;
+        };
+        uint32_t m = branch_metric(s_sym[0]);
+        for (uint32_t t = 0; t < steps; t++) {
+            const uint32_t wnext = s_sym[t + 1 < steps ? t + 1 : t];
+            const uint32_t mm = 63u - m;
+            // ACS (deconvolve.cpp:352-359); ties choose the upper predecessor (decision = 1)
+            const uint32_t t1 = __viaddmin_u32(B, mm, 255u), ne = __viaddmin_u32(A, m, t1);
+            const uint32_t t3 = __viaddmin_u32(B, m, 255u), no = __viaddmin_u32(A, mm, t3);
+            const uint32_t pair = __byte_perm(ne, no, 0x5410);  // {N[2L], N[2L+1]} as 16-bit halves
+            const uint32_t pa = __shfl_sync(0xffffffffu, pair, srcA), pb = __shfl_sync(0xffffffffu, pair, srcB);
+            const uint32_t be = __ballot_sync(0xffffffffu, ne == t1), bo = __ballot_sync(0xffffffffu, no == t3);
+            // Renormalize256 (deconvolve.cpp:407-412): new state 0 is `ne` of lane 0
+            const bool renorm = (t & 1u) && (__ballot_sync(0xffffffffu, ne > 150u) & 1u);
+            if (lane == 0) s_dec[t] = make_uint2(be, bo);
+            m = branch_metric(wnext);
+            A = __byte_perm(pa, 0u, half_sel);
+            B = __byte_perm(pb, 0u, half_sel);
+            if (renorm) {
+                A = A > 63u ? A - 63u : 0u;
+                B = B > 63u ? B - 63u : 0u;
+            }
+        }
+        __syncwarp();
+        // ChainBack (deconvolve.cpp:416-435) by lane 0, same 32-bit state register as the pair kernel:
+        // state = h >> 26; its decision is bit (state >> 1) of the even / odd ballot word.
+        if (lane == 0) {
+            uint8_t* o = out + f * outbytes;
+            uint32_t h = 0;
+            int t = (int)framebits - 1;
+            auto step = [&](const uint2 w, int tt) {
+                const uint32_t x = __funnelshift_r((h & 0x04000000u) ? w.y : w.x, 0u, h >> 27);
+                h = __funnelshift_r(h, x, 1);
+                if ((tt & 7) == 0) o[tt >> 3] = (uint8_t)(h >> 24);
+            };
+            for (; (t & 7) != 7 && t >= 0; t--) step(s_dec[t + 6], t);  // ragged top (framebits % 8 != 0)
+            for (; t >= 7; t -= 8) {  // 8 steps per iteration: the loads do not depend on the state
+                uint2 w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) w[j] = s_dec[t - j + 6];
+#pragma unroll
+                for (int j = 0; j < 8; j++) step(w[j], t - j);
+            }
+        }
+    }
+}
+
 // u32 -> u8 compaction for the QIRX one-word-per-symbol layout (low byte only, deconvolve.cpp:219-228)
 __global__ void __launch_bounds__(256) compact_symbols_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ outw,
                                                               size_t nquads) {
@@ -343,6 +433,25 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
     else
         viterbi_pair_kernel<false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
                                                                              framebits, 1u);
+    count_launch();
+    return cudaGetLastError();
+}
+
+size_t viterbi_warp_smem_bytes(uint32_t framebits) { return 12 * (size_t)(framebits + 6); }
+
+cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
+                                int num_sms, cudaStream_t stream) {
+    if (nframes == 0) return cudaSuccess;
+    const size_t smem = viterbi_warp_smem_bytes(framebits);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(viterbi_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const unsigned long long cap = (unsigned long long)num_sms * 32;
+    const unsigned grid = (unsigned)(nframes < cap ? nframes : cap);
+    viterbi_warp_kernel<<<grid, 32, smem, stream>>>(d_syms, d_out, nframes, framebits);
     count_launch();
     return cudaGetLastError();
 }
