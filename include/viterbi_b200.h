@@ -91,6 +91,17 @@ int rs_check_superframe_batch(const uint8_t* in, unsigned int RSDims, size_t n, 
 int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
                                      int32_t* d_ret, void* stream);
 
+/* DAB+ audio pipeline on the device: QIRX decodes five logical frames with
+ * deconvolve() and then hands the 5 * F/8 = 120 * s bytes to RScheckSuperframe() (exc_handler.cpp:34-36).
+ * These calls do both steps for nsf superframes without the host round trip in between:
+ * syms [nsf * 5][4*(F+6)] soft symbols -> Viterbi -> [nsf][120*s] superframes (s = F/192) -> RS check
+ * -> out [nsf][110*s] (same partial-write rule as RScheckSuperframe), ret [nsf].  framebits must be a
+ * multiple of 192.  (The DAB energy-dispersal descrambler that sits between the two calls in a full
+ * receiver is not part of viterbi.dll and is not applied.) */
+int dabplus_decode_superframes(unsigned int framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret);
+int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_syms, size_t nsf, uint8_t* d_out,
+                                      int32_t* d_ret, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Device selection and utilities (replace getcpucaps/setupdll per the design brief)
  * ------------------------------------------------------------------------------------------- */

@@ -112,3 +112,40 @@ def test_one_million_superframes_bit_exact(vb, checker):
         out, ret = vb.rs_check_superframe_batch(rx, s, fill=0xEE)
         assert np.array_equal(ret, want_ret), s
         assert np.array_equal(out, want_out), s
+
+
+# ---------------------------------------------------------------------------------------------------
+# Viterbi -> superframe -> RS on the device (BASELINE config 5 shape)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("framebits,nsf,ebn0,max_err", [(3072, 40, 2.0, 3), (3072, 900, 4.0, 7), (768, 700, 1.5, 2),
+                                                        (192, 1000, 3.0, 6), (1536, 64, 0.5, 0)])
+def test_dabplus_pipeline_matches_reference_chain(vb, checker, framebits, nsf, ebn0, max_err):
+    """deconvolve x5 then RScheckSuperframe, as QIRX chains them (exc_handler.cpp:34-36), vs one device call."""
+    import torch
+
+    s = framebits // 192
+    syms, payload, _ = dabgen.make_superframe_frames(nsf, framebits, ebn0, seed=framebits + nsf, max_err=max_err)
+    decoded = checker.deconvolve_batch(framebits, syms)  # [nsf*5, F/8] == [nsf, 120*s]
+    want_out, want_ret = checker.rs_batch(decoded.reshape(nsf, 120 * s), s, fill=0xEE)
+    out, ret = vb.dabplus_decode_superframes(framebits, syms, fill=0xEE)
+    assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out)
+    d_out = torch.full((nsf, 110 * s), 0xEE, dtype=torch.uint8, device="cuda")
+    d_out, d_ret = vb.dabplus_decode_superframes_device(framebits, torch.from_numpy(syms).cuda(), d_out)
+    assert np.array_equal(d_ret.cpu().numpy(), want_ret) and np.array_equal(d_out.cpu().numpy(), want_out)
+    if max_err == 0 and ebn0 >= 3.0:
+        assert np.array_equal(out, payload)
+
+
+def test_dabplus_pipeline_recovers_payload_end_to_end(vb):
+    """Encode -> RS -> interleave -> convolutional code -> noisy channel -> device pipeline == payload.
+    At 4 dB residual Viterbi errors are rare and within RS reach."""
+    syms, payload, _ = dabgen.make_superframe_frames(300, 3072, 4.0, seed=5, max_err=2)
+    out, ret = vb.dabplus_decode_superframes(3072, syms, fill=0xEE)
+    ok = ret >= 0
+    assert ok.mean() > 0.95
+    assert np.array_equal(out[ok], payload[ok])
+
+
+def test_dabplus_pipeline_argument_checks(vb):
+    assert vb.lib.dabplus_decode_superframes(100, None, 1, None, None) == vb.FEC_ERR_ARG  # not a multiple of 192
+    assert vb.lib.dabplus_decode_superframes(3072, None, 0, None, None) == vb.FEC_OK

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "viterbi_deconvolve_batch_u32_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
     "rs_check_superframe_batch": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp]),
     "rs_check_superframe_batch_device": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp, _vp]),
+    "dabplus_decode_superframes": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
+    "dabplus_decode_superframes_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp, _vp]),
     "fec_device_count": (ctypes.c_int, []),
     "fec_set_device": (ctypes.c_int, [ctypes.c_int]),
     "fec_get_device": (ctypes.c_int, []),
@@ -180,6 +182,32 @@ def rs_check_superframe_batch_device(rx, RSDims: int, out, ret=None, stream=None
     assert rx.is_contiguous() and out.is_contiguous() and ret.is_contiguous()
     rc = lib.rs_check_superframe_batch_device(rx.data_ptr(), RSDims, n, out.data_ptr(), ret.data_ptr(), _stream_ptr(stream))
     _check(rc, "rs_check_superframe_batch_device")
+    return out, ret
+
+
+def dabplus_decode_superframes(framebits: int, syms: np.ndarray, out: np.ndarray | None = None, fill: int = 0):
+    """syms [nsf*5, 4*(F+6)] u8 -> Viterbi -> RS check -> (out [nsf, 110*s], ret [nsf]), s = F/192."""
+    syms = np.ascontiguousarray(syms, dtype=np.uint8)
+    nsf, s = syms.shape[0] // 5, framebits // 192
+    assert syms.shape == (nsf * 5, 4 * (framebits + 6))
+    if out is None:
+        out = np.full((nsf, 110 * s), fill, dtype=np.uint8)
+    ret = np.zeros(nsf, dtype=np.int32)
+    _check(lib.dabplus_decode_superframes(framebits, _ptr(syms), nsf, _ptr(out), _ptr(ret)), "dabplus_decode_superframes")
+    return out, ret
+
+
+def dabplus_decode_superframes_device(framebits: int, syms, out, ret=None, stream=None):
+    """Device-resident pipeline: syms CUDA u8 [nsf*5, 4*(F+6)], out CUDA u8 [nsf, 110*s] (updated in place)."""
+    import torch
+
+    nsf = syms.shape[0] // 5
+    if ret is None:
+        ret = torch.empty((nsf,), dtype=torch.int32, device=syms.device)
+    assert syms.is_contiguous() and out.is_contiguous() and out.shape == (nsf, 110 * (framebits // 192))
+    rc = lib.dabplus_decode_superframes_device(framebits, syms.data_ptr(), nsf, out.data_ptr(), ret.data_ptr(),
+                                               _stream_ptr(stream))
+    _check(rc, "dabplus_decode_superframes_device")
     return out, ret
 
 

@@ -375,6 +375,73 @@ int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, s
                : FEC_OK;
 }
 
+// Viterbi -> superframe -> RS on the device.  Five consecutive decoded frames ARE one superframe
+// ([nsf*5][F/8] == [nsf][120*s] with s = F/192), so no regrouping pass is needed between the kernels.
+int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_syms, size_t nsf, uint8_t* d_out,
+                                      int32_t* d_ret, void* stream) {
+    if (!vit_args_ok(framebits) || framebits == 0 || framebits % 192u) return bad_arg("framebits must be a multiple of 192");
+    if (nsf == 0) return FEC_OK;
+    if (!d_syms || !d_out || !d_ret) return bad_arg("null pointer");
+    if (reinterpret_cast<uintptr_t>(d_syms) & 7) return bad_arg("d_syms must be 8-byte aligned");
+    DeviceState* st = device_state();
+    if (!st) return FEC_ERR_DEVICE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned rsdims = framebits / 192u;
+    void* d_bits = nullptr;
+    if (fail(cudaMallocAsync(&d_bits, nsf * 120 * (size_t)rsdims, s), "cudaMallocAsync(decoded frames)")) return FEC_ERR_DEVICE;
+    int rc = vit_device(st, framebits, d_syms, nsf * 5, (uint8_t*)d_bits, s, nullptr, 0);
+    if (rc == FEC_OK && fail(launch_rs_superframes((const uint8_t*)d_bits, d_out, d_ret, nsf, rsdims, st->num_sms, s),
+                             "rs kernel launch"))
+        rc = FEC_ERR_DEVICE;
+    (void)cudaFreeAsync(d_bits, s);
+    return rc;
+}
+
+int dabplus_decode_superframes(unsigned int framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret) {
+    if (!vit_args_ok(framebits) || framebits == 0 || framebits % 192u) return bad_arg("framebits must be a multiple of 192");
+    if (nsf == 0) return FEC_OK;
+    if (!syms || !out || !ret) return bad_arg("null pointer");
+    int dev;
+    DeviceState* st = device_state(&dev);
+    if (!st) return FEC_ERR_DEVICE;
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
+    const unsigned rsdims = framebits / 192u;
+    const size_t nsym = 4 * ((size_t)framebits + 6), in_row = 5 * nsym, out_row = 110 * (size_t)rsdims;
+    size_t chunk = (32u << 20) / in_row;
+    if (chunk < 1) chunk = 1;
+    if (chunk > nsf) chunk = nsf;
+    int rc = FEC_OK;
+    size_t done = 0;
+    for (int k = 0; done < nsf && rc == FEC_OK; k++) {
+        Slot& sl = g_pipe.slot[k % kPipe];
+        const size_t m = (nsf - done < chunk) ? nsf - done : chunk;
+        if (fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize")) { rc = FEC_ERR_DEVICE; break; }
+        if (!grow(&sl.d_in, &sl.in_cap, m * in_row) || !grow(&sl.d_out, &sl.out_cap, m * out_row) ||
+            !grow(&sl.d_aux, &sl.aux_cap, m * sizeof(int32_t))) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        if (fail(cudaMemcpyAsync(sl.d_in, syms + done * in_row, m * in_row, cudaMemcpyHostToDevice, sl.stream), "H2D") ||
+            fail(cudaMemcpyAsync(sl.d_out, out + done * out_row, m * out_row, cudaMemcpyHostToDevice, sl.stream), "H2D out")) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        rc = dabplus_decode_superframes_device(framebits, (const uint8_t*)sl.d_in, m, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux,
+                                               sl.stream);
+        if (rc != FEC_OK) break;
+        if (fail(cudaMemcpyAsync(out + done * out_row, sl.d_out, m * out_row, cudaMemcpyDeviceToHost, sl.stream), "D2H") ||
+            fail(cudaMemcpyAsync(ret + done, sl.d_aux, m * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ret")) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        done += m;
+    }
+    for (Slot& sl : g_pipe.slot)
+        if (sl.stream && fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // device selection and utilities
 // ---------------------------------------------------------------------------------------------

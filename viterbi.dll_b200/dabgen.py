@@ -248,3 +248,27 @@ def make_superframes_torch(n: int, s: int, seed: int, device, max_err: int = 7, 
         nerr_all[lo : lo + m] = nerr
     rx = rx.reshape(n, s, RS_N).transpose(1, 2).contiguous().reshape(n, RS_N * s)
     return rx, nerr_all.reshape(n, s)
+
+
+# ---------------------------------------------------------------------------
+# DAB+ pipeline traffic: RS-protected superframes carried in 5 convolutionally coded frames each
+# ---------------------------------------------------------------------------
+def make_superframe_frames(nsf: int, framebits: int, ebn0_db: float, seed: int, max_err: int = 0):
+    """-> (symbols u8 [nsf*5, 4*(F+6)], clean payload [nsf, 110*s], transmitted superframes [nsf, 120*s]).
+
+    A superframe of s = F/192 interleaved RS(120,110) codewords is 5*F/8 bytes = the payload of five
+    consecutive frames.  max_err > 0 additionally corrupts bytes BEFORE the convolutional encoder
+    (errors the Viterbi decoder cannot remove), so the RS stage has work even on a clean channel."""
+    if framebits % 192:
+        raise ValueError("framebits must be a multiple of 192")
+    s = framebits // 192
+    rng = np.random.default_rng(seed)
+    msg = rng.integers(0, 256, size=(nsf * s, RS_K), dtype=np.uint8)
+    cw = rs_encode(msg)
+    if max_err:
+        cw = rs_inject_errors(cw, rng.integers(0, max_err + 1, size=nsf * s), rng)
+    sf = rs_interleave(cw, s)  # [nsf, 120*s]
+    bits = np.unpackbits(sf.reshape(nsf * 5, framebits // 8), axis=1, bitorder="big")
+    syms = soft_symbols(conv_encode(bits), ebn0_db, rng)
+    payload = np.ascontiguousarray(msg.reshape(nsf, s, RS_K).transpose(0, 2, 1)).reshape(nsf, RS_K * s)
+    return syms, payload, sf
