@@ -397,6 +397,45 @@ def run_b200(args):
                          "d2h_bytes_per_step": sum(per_s * (110 * s + 4) for s in range(1, 9)),
                          "api": "rs_check_superframe_batch (pinned host buffers; outVector travels both ways)"}
 
+    # ---- extras: MSC batch (BASELINE configs[2] shape) and the on-device DAB+ pipeline (configs[4] shape) ----
+    extra = {}
+    if not args.no_extra:
+        def timed(fn, reps):
+            for _ in range(2):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)) / reps
+
+        mn, mf = args.msc_frames, 3072
+        msym, mbits = dabgen.make_frames_torch(mn, mf, 3.0, seed=4321 + rank, device=dev, want_bits=True)
+        mout = torch.zeros((mn, mf // 8), dtype=torch.uint8, device=dev)
+        ms_msc = timed(lambda: vb.deconvolve_batch_device(mf, msym, mout, stream), 5)
+        diff = (mout ^ mbits)
+        nbad = int((diff != 0).any(dim=1).sum().item())
+        extra["msc"] = {"workload": "batched MSC decode (BASELINE configs[2] shape): %d frames per GPU x F=3072, Eb/N0=3 dB" % mn,
+                        "value": mn * world * mf / (ms_msc * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": ms_msc,
+                        "roofline_int_alu_frac": W_VIT_OPS_PER_STEP * mn * (mf + 6) / (ms_msc * 1e-3) / 1e12 / int_peak,
+                        "frame_error_rate": nbad / mn}
+        # DAB+ pipeline on the first 5*k frames of the same symbols (payload is random, so most superframes
+        # fail RS: the point is the cost of the fused chain, parity is covered by tests/test_gpu_rs.py)
+        nsf = min(mn // 5, args.pipeline_superframes)
+        psym = msym[: nsf * 5]
+        pout = torch.full((nsf, 110 * 16), 0xEE, dtype=torch.uint8, device=dev)
+        pret = torch.empty((nsf,), dtype=torch.int32, device=dev)
+        ms_pipe = timed(lambda: vb.dabplus_decode_superframes_device(mf, psym, pout, pret, stream), 5)
+        extra["dabplus_pipeline"] = {"workload": "%d MSC frames -> %d superframes (s=16) per GPU: Viterbi + RS check on device" % (nsf * 5, nsf),
+                                     "superframes_per_s": nsf * world / (ms_pipe * 1e-3),
+                                     "viterbi_gbit_per_s": nsf * 5 * world * mf / (ms_pipe * 1e-3) / 1e9, "ms_per_step": ms_pipe}
+        del msym, mout, mbits, psym
+        torch.cuda.empty_cache()
+
     # ---- gather of result bitstreams over NCCL (outside the timed region) -----------------------------
     gather_ms = None
     if world > 1:
@@ -448,6 +487,7 @@ def run_b200(args):
                        "l2_policy": "input %d MB + decision scratch > 126 MB L2; no explicit flush" % (n * nsym // 1000000)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline,
             "roofline_int_alu": roofline_int, "cpu_baseline": cpu, "rs": rs, "frame_error_rate": fer, "gather_ms": gather_ms,
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
@@ -468,6 +508,9 @@ def main():
     ap.add_argument("--no-rs", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the MSC and DAB+ pipeline side measurements")
+    ap.add_argument("--msc-frames", type=int, default=262144)
+    ap.add_argument("--pipeline-superframes", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
