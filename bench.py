@@ -268,11 +268,13 @@ def run_b200(args):
     launches0 = vb.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
+        torch.cuda.nvtx.range_push("fec_timed_viterbi")  # ncu --nvtx --nvtx-include "fec_timed_viterbi/" = the timed region
         e0.record(stream)
         for _ in range(args.steps):
             vit_step()
         e1.record(stream)
         torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
     launches = vb.kernel_launches() - launches0
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -353,11 +355,13 @@ def run_b200(args):
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = vb.kernel_launches()
+        torch.cuda.nvtx.range_push("fec_timed_rs")
         r0.record(stream)
         for _ in range(args.steps):
             rs_step()
         r1.record(stream)
         torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
         rs_launches = vb.kernel_launches() - l0
         barrier()
         rs_ms = max_over_ranks(r0.elapsed_time(r1)) / args.steps
