@@ -44,16 +44,31 @@ enum Op {
     OP_ACS_CORE,          // the 3-op ACS body: t=min(B+mm,255); n=min(A+m,t); d=n+K-t
     OP_SHFL,
     OP_BALLOT,
+    OP_HSET2,        // set.eq.f16x2.f16x2 (HSET2.BF)
+    OP_HFMA2,        // fma.rn.f16x2
+    OP_ACS_FP16FLAG, // proposed ACS core: 2x VIADDMNMX (ALU) + HSET2.BF.EQ + HFMA2 flag accumulate
+    OP_ACS_PREDIMAD, // current ACS core: VIADDMNMX + IMAD + VIMNMX(preds) + 2 predicated IMAD
+    OP_ACS_PREDFADD, // variant: decision bits accumulated with predicated FADD (fmalite-capable)
+    OP_FADD,
+    OP_VIMNMX_PRED,       // VIMNMX.U16x2 with predicate outputs only
+    OP_ADDMIN_MINPRED,    // VIADDMNMX + VIMNMX.P (2 ALU), predicates dropped
+    OP_PRED_IMAD_REG,     // 2 ALU + 2 predicated IMAD with register weight
+    OP_PRED_IADD,         // 2 ALU + 2 predicated add with immediate (ptxas picks the pipe)
+    OP_VIADD_IMM,         // add.u32 with immediate (VIADD)
+    OP_VIADD_IMM_PLUS_ALU,// VIADD + VIADDMNMX
+    OP_VIADD_IMM_PLUS_IMAD,// VIADD + IMAD
     OP_COUNT
 };
 
 static const char* op_name[OP_COUNT] = {
     "iadd", "lop3", "imad", "shf", "prmt", "mnmx_u32", "viadd_16x2", "vimnmx_u16x2", "vimnmx3_u16x2",
     "viaddmnmx_u16x2", "viaddmnmx_u32", "mix_iadd_lop3", "mix_viaddmnmx_imad", "mix_viaddmnmx_iadd3",
-    "mix_viaddmnmx_lop3", "acs_core_3op", "shfl_xor", "ballot"};
+    "mix_viaddmnmx_lop3", "acs_core_3op", "shfl_xor", "ballot", "hset2_bf_eq", "hfma2", "acs_fp16flag_4op",
+    "acs_predimad_4op", "acs_predfadd_4op", "fadd", "vimnmx_pred", "addmin_minpred_2op", "acs_predimad_reg_4op",
+    "acs_prediadd_4op", "viadd_imm", "viadd_imm+viaddmnmx", "viadd_imm+imad"};
 // SASS instructions per chain-iteration (ptxas fuses two dependent add/min steps into one
 // IADD3 / VIMNMX3, hence 0.5 for those three)
-static const double op_count[OP_COUNT] = {0.5, 1, 1, 1, 1, 0.5, 1, 0.5, 1, 1, 1, 2, 2, 2, 2, 3, 1, 3};
+static const double op_count[OP_COUNT] = {0.5, 1, 1, 1, 1, 0.5, 1, 0.5, 1, 1, 1, 2, 2, 2, 2, 3, 1, 3, 1, 1, 4, 4, 4, 1, 1, 2, 4, 4, 1, 2, 2};
 
 template <int OP>
 __device__ __forceinline__ uint32_t step(uint32_t x, uint32_t a, uint32_t b) {
@@ -90,15 +105,104 @@ __device__ __forceinline__ uint32_t step(uint32_t x, uint32_t a, uint32_t b) {
         uint32_t n = __viaddmin_u16x2(a, b, t);
         return n + 0x80008000u - t;
     }
+    if (OP == OP_HSET2) { asm volatile("set.eq.f16x2.f16x2 %0, %0, %1;" : "+r"(x) : "r"(a)); return x; }
+    if (OP == OP_HFMA2) { asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)); return x; }
+    if (OP == OP_VIADD_IMM) { asm volatile("add.u32 %0, %0, 0x12345;" : "+r"(x)); return x; }
+    if (OP == OP_VIADD_IMM_PLUS_ALU) { asm volatile("add.u32 %0, %0, 0x12345;" : "+r"(x)); return __viaddmin_u16x2(x, a, b); }
+    if (OP == OP_VIADD_IMM_PLUS_IMAD) {
+        asm volatile("add.u32 %0, %0, 0x12345;" : "+r"(x));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+        return x;
+    }
     if (OP == OP_SHFL) return __shfl_xor_sync(0xffffffffu, x, 1);
     if (OP == OP_BALLOT) return __ballot_sync(0xffffffffu, (int)x < 0) + a;
     return x;
+}
+
+__device__ __forceinline__ uint32_t acs_fp16flag(uint32_t x, uint32_t a, uint32_t b, uint32_t& acc) {
+    uint32_t t = __viaddmin_u16x2(x, b, 0x0FF00FF0u);
+    uint32_t n = __viaddmin_u16x2(a, b, t);
+    uint32_t f;
+    asm volatile("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(f) : "r"(n), "r"(t));
+    asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(f), "r"(0x40004000u));
+    return n;
+}
+__device__ __forceinline__ uint32_t acs_predimad(uint32_t x, uint32_t a, uint32_t b, uint32_t& accA, uint32_t& accB,
+                                                 uint32_t one) {
+    uint32_t t = __viaddmin_u16x2(x, b, 0x0FF00FF0u);
+    uint32_t m0, n;
+    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(m0) : "r"(a), "r"(one), "r"(b));
+    asm volatile("{.reg .pred pu, pv; .reg .u16 rs0, rs1, rs2, rs3;\n\t"
+                 "min.u16x2 %0, %3, %4;\n\t"
+                 "mov.b32 {rs0, rs1}, %0;\n\t"
+                 "mov.b32 {rs2, rs3}, %3;\n\t"
+                 "setp.eq.u16 pv, rs0, rs2;\n\t"
+                 "setp.eq.u16 pu, rs1, rs3;\n\t"
+                 "@pv mad.lo.u32 %1, %5, 2, %1;\n\t"
+                 "@pu mad.lo.u32 %2, %5, 2, %2;}\n\t"
+                 : "=r"(n), "+r"(accA), "+r"(accB)
+                 : "r"(t), "r"(m0), "r"(one));
+    return n;
+}
+
+__device__ __forceinline__ uint32_t acs_predfadd(uint32_t x, uint32_t a, uint32_t b, float& accA, float& accB,
+                                                 uint32_t one) {
+    uint32_t t = __viaddmin_u16x2(x, b, 0x0FF00FF0u);
+    uint32_t m0, n;
+    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(m0) : "r"(a), "r"(one), "r"(b));
+    asm volatile("{.reg .pred pu, pv; .reg .u16 rs0, rs1, rs2, rs3;\n\t"
+                 "min.u16x2 %0, %3, %4;\n\t"
+                 "mov.b32 {rs0, rs1}, %0;\n\t"
+                 "mov.b32 {rs2, rs3}, %3;\n\t"
+                 "setp.eq.u16 pv, rs0, rs2;\n\t"
+                 "setp.eq.u16 pu, rs1, rs3;\n\t"
+                 "@pv add.rn.f32 %1, %1, 0f40000000;\n\t"
+                 "@pu add.rn.f32 %2, %2, 0f40000000;}\n\t"
+                 : "=r"(n), "+f"(accA), "+f"(accB)
+                 : "r"(t), "r"(m0));
+    return n;
+}
+
+#define MINPRED_HEAD                                         \
+    "{.reg .pred pu, pv; .reg .u16 rs0, rs1, rs2, rs3;\n\t" \
+    "min.u16x2 %0, %3, %4;\n\t"                             \
+    "mov.b32 {rs0, rs1}, %0;\n\t"                           \
+    "mov.b32 {rs2, rs3}, %3;\n\t"                           \
+    "setp.eq.u16 pv, rs0, rs2;\n\t"                         \
+    "setp.eq.u16 pu, rs1, rs3;\n\t"
+template <int MODE>
+__device__ __forceinline__ uint32_t acs_generic(uint32_t x, uint32_t a, uint32_t b, uint32_t& accA, uint32_t& accB,
+                                                uint32_t one, uint32_t wreg) {
+    uint32_t n;
+    if (MODE == 0) {  // VIMNMX.P only; each predicate has one cheap consumer so it is not optimised away
+        asm volatile(MINPRED_HEAD "@pv mov.u32 %1, %3;\n\t@pu mov.u32 %2, %3;}\n\t"
+                     : "=r"(n), "+r"(accA), "+r"(accB) : "r"(x), "r"(a));
+        return n;
+    }
+    uint32_t t = __viaddmin_u16x2(x, b, 0x0FF00FF0u);
+    if (MODE == 1) {
+        asm volatile(MINPRED_HEAD "}\n\t" : "=r"(n), "+r"(accA), "+r"(accB) : "r"(t), "r"(a));
+    } else if (MODE == 2) {
+        asm volatile(MINPRED_HEAD "@pv mad.lo.u32 %1, %5, %6, %1;\n\t@pu mad.lo.u32 %2, %5, %6, %2;}\n\t"
+                     : "=r"(n), "+r"(accA), "+r"(accB) : "r"(t), "r"(a), "r"(one), "r"(wreg));
+    } else {
+        asm volatile(MINPRED_HEAD "@pv add.u32 %1, %1, 2;\n\t@pu add.u32 %2, %2, 2;}\n\t"
+                     : "=r"(n), "+r"(accA), "+r"(accB) : "r"(t), "r"(a));
+    }
+    return n;
 }
 
 template <int OP>
 __global__ void __launch_bounds__(256) bench(uint32_t* out, uint32_t seed_a, uint32_t seed_b, int iters,
                                              long long* cycles) {
     uint32_t x[CHAINS];
+    uint32_t accs[CHAINS], accs2[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) accs[c] = 0x64006400u, accs2[c] = 0;
+    const uint32_t one = (seed_a >> 1);  // seed_a == 3 -> 1, opaque to the compiler
+    float fa[CHAINS], fb[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) fa[c] = 8388608.0f, fb[c] = 8388608.0f;
     uint32_t a = seed_a + threadIdx.x, b = seed_b ^ (threadIdx.x * 2654435761u);
     if (OP == OP_MNMX32 || OP == OP_VMNMX16 || OP == OP_VMNMX3_16) { a |= 0xFFF0FFF0u; b |= 0xFF00FF00u; }
 #pragma unroll
@@ -108,13 +212,23 @@ __global__ void __launch_bounds__(256) bench(uint32_t* out, uint32_t seed_a, uin
 #pragma unroll
         for (int u = 0; u < 8; u++) {
 #pragma unroll
-            for (int c = 0; c < CHAINS; c++) x[c] = step<OP>(x[c], a, b);
+            for (int c = 0; c < CHAINS; c++) {
+                if (OP == OP_ACS_FP16FLAG) x[c] = acs_fp16flag(x[c], a, b, accs[c]);
+                else if (OP == OP_ACS_PREDIMAD) x[c] = acs_predimad(x[c], a, b, accs[c], accs2[c], one);
+                else if (OP == OP_ACS_PREDFADD) x[c] = acs_predfadd(x[c], a, b, fa[c], fb[c], one);
+                else if (OP == OP_VIMNMX_PRED) x[c] = acs_generic<0>(x[c], a, b, accs[c], accs2[c], one, seed_b);
+                else if (OP == OP_ADDMIN_MINPRED) x[c] = acs_generic<1>(x[c], a, b, accs[c], accs2[c], one, seed_b);
+                else if (OP == OP_PRED_IMAD_REG) x[c] = acs_generic<2>(x[c], a, b, accs[c], accs2[c], one, seed_b);
+                else if (OP == OP_PRED_IADD) x[c] = acs_generic<3>(x[c], a, b, accs[c], accs2[c], one, seed_b);
+                else if (OP == OP_FADD) { asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(fa[c]) : "f"(fb[c])); }
+                else x[c] = step<OP>(x[c], a, b);
+            }
         }
     }
     long long t1 = clock64();
     uint32_t acc = 0;
 #pragma unroll
-    for (int c = 0; c < CHAINS; c++) acc ^= x[c];
+    for (int c = 0; c < CHAINS; c++) acc ^= x[c] ^ accs[c] ^ accs2[c] ^ __float_as_uint(fa[c]) ^ __float_as_uint(fb[c]);
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -180,5 +294,18 @@ int main(int argc, char** argv) {
     run<OP_ACS_CORE>(nsm, iters, d_out, d_cyc, h_cyc);
     run<OP_SHFL>(nsm, iters, d_out, d_cyc, h_cyc);
     run<OP_BALLOT>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_HSET2>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_HFMA2>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_ACS_FP16FLAG>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_ACS_PREDIMAD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_ACS_PREDFADD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_FADD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VIMNMX_PRED>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_ADDMIN_MINPRED>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_PRED_IMAD_REG>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_PRED_IADD>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VIADD_IMM>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VIADD_IMM_PLUS_ALU>(nsm, iters, d_out, d_cyc, h_cyc);
+    run<OP_VIADD_IMM_PLUS_IMAD>(nsm, iters, d_out, d_cyc, h_cyc);
     return 0;
 }

@@ -16,8 +16,8 @@
 //     (e + f) & 0x03F0 without a shift.
 //   * decisions: 64 bits per step per frame.  The survivor select is a packed min that also
 //     returns one predicate per frame (VIMNMX.U16x2 with predicate outputs); each predicate adds
-//     its decision bit to a per-frame 64-bit word with a predicated IMAD, which runs on the FMA
-//     pipe and so overlaps the ALU-pipe min/add-min work.  The words are streamed to a per-warp
+//     its decision bit to a per-frame 64-bit word with a predicated VIADD, which issues beside the
+//     ALU-pipe min/add-min work instead of competing with it.  The words are streamed to a per-warp
 //     scratch area in global memory, fully coalesced (512 B per warp per step).
 //     Shared memory cannot hold them: 8 B x 3078 steps = 24.6 KB per frame would cap an SM at
 //     9 frames.
@@ -50,19 +50,13 @@ constexpr uint32_t kSat = 0x0FF00FF0u;    // 255 * 16 per half: paddusb ceiling
 constexpr uint32_t kM63 = 0x03F003F0u;    // 63 * 16 per half
 constexpr uint32_t kEven = 0xFFFEFFFEu;
 
-// a + b on the FMA pipe: IMAD with a multiplier the compiler cannot fold (`one` is a kernel argument
-// that is always 1).  ptxas would otherwise emit IADD3 and put the add on the already saturated ALU pipe.
-__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) {
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
-    return d;
-}
-
 // ne = min(t, m0) per 16-bit half, and for each half whose minimum is t (ties included) add `bit` to
 // that frame's decision word.  ptxas fuses the min + setp pattern into one VIMNMX.U16x2 with two
-// predicate outputs (the same pattern __vibmin_u16x2 uses) and keeps the adds as predicated IMADs.
-__device__ __forceinline__ uint32_t min_decide(uint32_t t, uint32_t m0, uint32_t& decA, uint32_t& decB, uint32_t one,
-                                               uint32_t bit) {
+// predicate outputs (the same pattern __vibmin_u16x2 uses) and emits the adds as predicated VIADD,
+// which does not occupy the ALU pipe the min / add-min instructions run on (measured:
+// VIADD + VIADDMNMX pairs issue at 1.0 instruction/clk per SM sub-partition, profiles/intbench_r01b.jsonl;
+// a predicated IMAD in the same place was 12-15 % slower end to end).
+__device__ __forceinline__ uint32_t min_decide(uint32_t t, uint32_t m0, uint32_t& decA, uint32_t& decB, uint32_t bit) {
     uint32_t ne;
     asm("{.reg .pred pu, pv; .reg .u16 rs0, rs1, rs2, rs3;\n\t"
         "min.u16x2 %0, %3, %4;\n\t"
@@ -70,10 +64,10 @@ __device__ __forceinline__ uint32_t min_decide(uint32_t t, uint32_t m0, uint32_t
         "mov.b32 {rs2, rs3}, %3;\n\t"
         "setp.eq.u16 pv, rs0, rs2;\n\t"
         "setp.eq.u16 pu, rs1, rs3;\n\t"
-        "@pv mad.lo.u32 %1, %5, %6, %1;\n\t"
-        "@pu mad.lo.u32 %2, %5, %6, %2;}\n\t"
+        "@pv add.u32 %1, %1, %5;\n\t"
+        "@pu add.u32 %2, %2, %5;}\n\t"
         : "=r"(ne), "+r"(decA), "+r"(decB)
-        : "r"(t), "r"(m0), "r"(one), "r"(bit));
+        : "r"(t), "r"(m0), "r"(bit));
     return ne;
 }
 
@@ -82,8 +76,7 @@ __device__ __forceinline__ uint32_t min_decide(uint32_t t, uint32_t m0, uint32_t
 // With a = (x0+x1+1)>>1 and b = (x2+x3+1)>>1:  16*m = (2a + 2b + 2) & 0x3F0.
 // x ^ 0xFF = 255 - x, so the four (T0,T1) cases of x0+x1+1 are linear in y0+y1 or y0-y1.
 // wA / wB: the four soft symbols of one trellis step of frame A / frame B.
-__device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_t (&bm)[8], uint32_t (&bmm)[8],
-                                               uint32_t one) {
+__device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_t (&bm)[8], uint32_t (&bmm)[8]) {
     const uint32_t p01 = __byte_perm(wA, wB, 0x5140);  // A0 B0 A1 B1
     const uint32_t p23 = __byte_perm(wA, wB, 0x7362);  // A2 B2 A3 B3
     const uint32_t y0 = __byte_perm(p01, 0u, 0x4140), y1 = __byte_perm(p01, 0u, 0x4342);
@@ -102,7 +95,7 @@ __device__ __forceinline__ void branch_metrics(uint32_t wA, uint32_t wB, uint32_
 #pragma unroll
     for (int p = 0; p < 8; p++) {
         const int t0 = p & 1, t1 = (p >> 1) & 1, t2 = (p >> 2) & 1;
-        bm[p] = fma_add(e[t0][t1], f[t2][t0], one) & kM63;
+        bm[p] = (e[t0][t1] + f[t2][t0]) & kM63;
         bmm[p] = kM63 - bm[p];
     }
 }
@@ -128,19 +121,20 @@ __device__ __forceinline__ uint32_t renorm_addend(uint32_t m0) {
 // 32-63; z,w = frame B; bit s = decision of new state s.
 //
 // The file is compiled with ptxas -O1, which keeps this source order, so the loop is software
-// pipelined by hand: the add / add-min stage of butterfly i+1 (2 ALU + 2 FMA-pipe instructions) is
-// issued between the two select stages of butterfly i (2 ALU + 4 FMA-pipe), which keeps both pipes
-// fed and puts 4+ independent instructions between every producer and its consumer.
+// pipelined by hand: the add / add-min stage of butterfly i+1 (2 add-mins + 2 adds) is issued between
+// the two select stages of butterfly i (2 mins + 4 predicated adds), which keeps the ALU pipe and the
+// pipe the plain adds use both fed and puts 4+ independent instructions between every producer and
+// its consumer.
 template <bool kRenorm>
 __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)[64], uint32_t wA, uint32_t wB,
-                                          uint32_t one, uint32_t neg) {
+                                          uint32_t neg) {
     constexpr int kPat[32] = {pattern(0),  pattern(1),  pattern(2),  pattern(3),  pattern(4),  pattern(5),  pattern(6),
                               pattern(7),  pattern(8),  pattern(9),  pattern(10), pattern(11), pattern(12), pattern(13),
                               pattern(14), pattern(15), pattern(16), pattern(17), pattern(18), pattern(19), pattern(20),
                               pattern(21), pattern(22), pattern(23), pattern(24), pattern(25), pattern(26), pattern(27),
                               pattern(28), pattern(29), pattern(30), pattern(31)};
     uint32_t bm[8], bmm[8];
-    branch_metrics(wA, wB, bm, bmm, one);
+    branch_metrics(wA, wB, bm, bmm);
     uint32_t dA[2] = {0u, 0u}, dB[2] = {0u, 0u};
     uint32_t t1[2], t3[2], m0[2], m2[2];
     {
@@ -150,9 +144,9 @@ __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)
             b = __viaddmax_s16x2_relu(b, neg, neg);
         }
         t1[0] = __viaddmin_u16x2(b, bmm[kPat[0]], kSat);
-        m0[0] = fma_add(a, bm[kPat[0]], one);
+        m0[0] = a + bm[kPat[0]];
         t3[0] = __viaddmin_u16x2(b, bm[kPat[0]], kSat);
-        m2[0] = fma_add(a, bmm[kPat[0]], one);
+        m2[0] = a + bmm[kPat[0]];
     }
 #pragma unroll
     for (int i = 0; i < 32; i++) {
@@ -162,16 +156,16 @@ __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)
             a = M[i + 1], b = M[i + 33];
             if (kRenorm) a = __viaddmax_s16x2_relu(a, neg, neg);
         }
-        N[2 * i] = min_decide(t1[c], m0[c], dA[w], dB[w], one, 1u << ((2 * i) & 31));
+        N[2 * i] = min_decide(t1[c], m0[c], dA[w], dB[w], 1u << ((2 * i) & 31));
         if (i + 1 < 32) {
             if (kRenorm) b = __viaddmax_s16x2_relu(b, neg, neg);
             t1[n] = __viaddmin_u16x2(b, bmm[kPat[(i + 1) & 31]], kSat);
-            m0[n] = fma_add(a, bm[kPat[(i + 1) & 31]], one);
+            m0[n] = a + bm[kPat[(i + 1) & 31]];
         }
-        N[2 * i + 1] = min_decide(t3[c], m2[c], dA[w], dB[w], one, 1u << ((2 * i + 1) & 31));
+        N[2 * i + 1] = min_decide(t3[c], m2[c], dA[w], dB[w], 1u << ((2 * i + 1) & 31));
         if (i + 1 < 32) {
             t3[n] = __viaddmin_u16x2(b, bm[kPat[(i + 1) & 31]], kSat);
-            m2[n] = fma_add(a, bmm[kPat[(i + 1) & 31]], one);
+            m2[n] = a + bmm[kPat[(i + 1) & 31]];
         }
     }
     return make_uint4(dA[0], dA[1], dB[0], dB[1]);
@@ -268,7 +262,7 @@ __device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_
 template <bool kWordStores>
 __global__ void __launch_bounds__(kVitThreads, kVitMinBlocks)
 viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
-                    unsigned long long nframes, uint32_t framebits, uint32_t one) {
+                    unsigned long long nframes, uint32_t framebits) {
     const uint32_t steps = framebits + 6;  // framebits is even: 2 * ((F + 6) / 2) == F + 6
     const size_t rowbytes = (size_t)4 * steps, outbytes = (framebits + 7) / 8;
     const uint32_t lane = threadIdx.x & 31u;
@@ -300,8 +294,8 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
         for (uint32_t t = 0; t < steps; t += 2) {
             uint2 na0 = a0, nb0 = b0;
             if (t + 2 < steps) na0 = __ldg(rowA + (t >> 1) + 1), nb0 = __ldg(rowB + (t >> 1) + 1);
-            dec[(size_t)(t + 0) * 32] = acs_step<true>(X, Y, a0.x, b0.x, one, neg);
-            dec[(size_t)(t + 1) * 32] = acs_step<false>(Y, X, a0.y, b0.y, one, 0u);
+            dec[(size_t)(t + 0) * 32] = acs_step<true>(X, Y, a0.x, b0.x, neg);
+            dec[(size_t)(t + 1) * 32] = acs_step<false>(Y, X, a0.y, b0.y, 0u);
             neg = renorm_addend(X[0]);
             a0 = na0, b0 = nb0;
         }
@@ -429,10 +423,10 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
     if (e != cudaSuccess) return e;
     if (framebits % 32 == 0)
         viterbi_pair_kernel<true><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                            framebits, 1u);
+                                                                            framebits);
     else
         viterbi_pair_kernel<false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                             framebits, 1u);
+                                                                             framebits);
     count_launch();
     return cudaGetLastError();
 }
