@@ -38,6 +38,13 @@ struct RsTables {
 
 __constant__ RsTables c_tables;
 
+// Block-shared copies of the tables.  They are file-scope __shared__ objects (not pointers handed down
+// through function arguments) so that every lookup compiles to an LDS with an immediate offset.
+__shared__ uint4 s_lfsr[256];
+__shared__ uint8_t s_ato[768];
+__shared__ uint8_t s_iof[256];
+__shared__ uint8_t s_mulpow[NROOTS * 256];
+
 // rschecksf.cpp:50-52
 __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u) >> 24; }
 
@@ -51,8 +58,8 @@ __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u)
 // stay zero under the multiplication.  A degree-d polynomial has at most d roots, so running past a
 // lane's own early-exit point cannot change its count.
 template <int D>
-__device__ __forceinline__ int chien(const uint8_t (&lam_poly)[NROOTS + 1], const uint8_t* __restrict__ mulpow,
-                                     uint8_t (&root)[NROOTS + 1], int deg, unsigned mask) {
+__device__ __forceinline__ int chien(const uint32_t (&lam_poly)[NROOTS + 1], uint32_t (&root)[NROOTS + 1], int deg,
+                                     unsigned mask) {
     uint32_t term[D];
 #pragma unroll
     for (int j = 0; j < D; j++) term[j] = lam_poly[j + 1];
@@ -61,13 +68,13 @@ __device__ __forceinline__ int chien(const uint8_t (&lam_poly)[NROOTS + 1], cons
         uint32_t q = 1;
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            term[j] = mulpow[j * 256 + term[j]];
+            term[j] = s_mulpow[j * 256 + term[j]];
             q ^= term[j];
         }
         if (q == 0 && count < deg) {
 #pragma unroll
             for (int c = 0; c < NROOTS; c++)
-                if (c == count) root[c] = (uint8_t)i;
+                if (c == count) root[c] = (uint32_t)i;
             count++;
         }
         if ((i & 7) == 0 && !__any_sync(mask, count < deg)) break;  // every lane has all its roots
@@ -80,9 +87,10 @@ __device__ __forceinline__ int chien(const uint8_t (&lam_poly)[NROOTS + 1], cons
 // uncorrectable.  Called by all lanes of `mask` together: control flow is kept warp-uniform (clean
 // lanes ride along with all-zero syndromes, which Berlekamp-Massey turns into lambda = 1, degree 0,
 // zero roots, return value 0 -- exactly the reference's early return).
-__device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __restrict__ ato,
-                                const uint8_t* __restrict__ iof, const uint4* __restrict__ lfsr,
-                                const uint8_t* __restrict__ mulpow, unsigned mask) {
+__device__ int rs_decode_column(uint8_t* col, uint32_t stride, unsigned mask) {
+    const uint8_t* const ato = s_ato;
+    const uint8_t* const iof = s_iof;
+    const uint4* const lfsr = s_lfsr;
     // ---- remainder of cw(x) mod g(x); cw[0] is the highest-degree coefficient -----------------
     uint32_t r0 = 0, r1 = 0, r2 = 0;  // coefficients x^0..x^3 | x^4..x^7 | x^8,x^9
 #pragma unroll 4
@@ -100,7 +108,7 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
     if (!__any_sync(mask, (r0 | r1 | r2) != 0u)) return 0;
 
     // ---- syndromes S_i = rem(alpha^i), then index form (rschecksf.cpp:232-233) ------------------
-    uint8_t syn[NROOTS];
+    uint32_t syn[NROOTS];  // 32-bit holders: byte arrays make the compiler pack/unpack registers
     {
         uint32_t lg[NROOTS];
 #pragma unroll
@@ -119,7 +127,7 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
     }
 
     // ---- Berlekamp-Massey (rschecksf.cpp:236-284): lambda polynomial form, b / syn index form ---
-    uint8_t lam[NROOTS + 1], b[NROOTS + 1], nxt[NROOTS + 1];
+    uint32_t lam[NROOTS + 1], b[NROOTS + 1], nxt[NROOTS + 1];
 #pragma unroll
     for (int i = 0; i <= NROOTS; i++) {
         lam[i] = (i == 0) ? 1 : 0;
@@ -148,7 +156,7 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
                 el = r - el;
 #pragma unroll
                 for (int i = 0; i <= NROOTS; i++)
-                    b[i] = (lam[i] == 0) ? (uint8_t)NN : (uint8_t)mod255(iof[lam[i]] - discr + NN);
+                    b[i] = (lam[i] == 0) ? (uint32_t)NN : mod255(iof[lam[i]] - discr + NN);
             } else {
 #pragma unroll
                 for (int i = NROOTS; i > 0; i--) b[i] = b[i - 1];
@@ -159,7 +167,7 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
         }
     }
 
-    uint8_t lam_poly[NROOTS + 1];
+    uint32_t lam_poly[NROOTS + 1];
     int deg_lambda = 0;
 #pragma unroll
     for (int i = 0; i <= NROOTS; i++) {
@@ -169,33 +177,33 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
     }
 
     // ---- Chien search, one instantiation per warp (largest degree present) ---------------------------
-    uint8_t root[NROOTS + 1];
+    uint32_t root[NROOTS + 1];
     int count = 0;
     switch (__reduce_max_sync(mask, (unsigned)deg_lambda)) {
-        case 1: count = chien<1>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 2: count = chien<2>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 3: count = chien<3>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 4: count = chien<4>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 5: count = chien<5>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 6: count = chien<6>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 7: count = chien<7>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 8: count = chien<8>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 9: count = chien<9>(lam_poly, mulpow, root, deg_lambda, mask); break;
-        case 10: count = chien<10>(lam_poly, mulpow, root, deg_lambda, mask); break;
+        case 1: count = chien<1>(lam_poly, root, deg_lambda, mask); break;
+        case 2: count = chien<2>(lam_poly, root, deg_lambda, mask); break;
+        case 3: count = chien<3>(lam_poly, root, deg_lambda, mask); break;
+        case 4: count = chien<4>(lam_poly, root, deg_lambda, mask); break;
+        case 5: count = chien<5>(lam_poly, root, deg_lambda, mask); break;
+        case 6: count = chien<6>(lam_poly, root, deg_lambda, mask); break;
+        case 7: count = chien<7>(lam_poly, root, deg_lambda, mask); break;
+        case 8: count = chien<8>(lam_poly, root, deg_lambda, mask); break;
+        case 9: count = chien<9>(lam_poly, root, deg_lambda, mask); break;
+        case 10: count = chien<10>(lam_poly, root, deg_lambda, mask); break;
         default: break;  // every lane has degree 0: nothing to search
     }
     if (deg_lambda != count) return -1;  // rschecksf.cpp:325-326
 
     // ---- omega(x) = syn(x) lambda(x) mod x^10, index form (rschecksf.cpp:331-341) ----------------
     const int deg_omega = deg_lambda - 1;
-    uint8_t om[NROOTS];
+    uint32_t om[NROOTS];
 #pragma unroll
     for (int i = 0; i < NROOTS; i++) {
         uint32_t tmp = 0;
 #pragma unroll
         for (int j = 0; j <= i; j++)
             if (syn[i - j] != NN && lam[j] != NN) tmp ^= ato[syn[i - j] + lam[j]];
-        om[i] = (i <= deg_omega) ? iof[tmp] : (uint8_t)NN;
+        om[i] = (i <= deg_omega) ? (uint32_t)iof[tmp] : (uint32_t)NN;
     }
 
     // ---- Forney (rschecksf.cpp:346-374) ---------------------------------------------------------
@@ -223,17 +231,13 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, const uint8_t* __
 
 }  // namespace
 
-// One block = `sf_per_block` whole superframes; dynamic shared memory:
-//   [tables: lfsr 4096 | ato 768 | iof 256 | mulpow 2560] [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
+// One block = `sf_per_block` whole superframes; static shared memory holds the tables (7.5 KB), dynamic:
+//   [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
 __global__ void __launch_bounds__(kRsThreads)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
                      unsigned long long nsf, uint32_t s, uint32_t sf_per_block) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint4* s_lfsr = reinterpret_cast<uint4*>(smem);
-    uint8_t* s_ato = smem + 4096;
-    uint8_t* s_iof = s_ato + 768;
-    uint8_t* s_mulpow = s_iof + 256;
-    int* s_fail = reinterpret_cast<int*>(s_mulpow + NROOTS * 256);
+    int* s_fail = reinterpret_cast<int*>(smem);
     int* s_sum = s_fail + sf_per_block;
     uint8_t* tile = reinterpret_cast<uint8_t*>(s_sum + sf_per_block);
     tile += (16 - (reinterpret_cast<uintptr_t>(tile) & 15)) & 15;
@@ -272,7 +276,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
             const unsigned mask = __ballot_sync(0xffffffffu, c < ncw);
             if (c < ncw) {
                 const uint32_t n = c / s, j = c - n * s;
-                const int r = rs_decode_column(tile + n * sf_in + j, s, s_ato, s_iof, s_lfsr, s_mulpow, mask);
+                const int r = rs_decode_column(tile + n * sf_in + j, s, mask);
                 if (r < 0)
                     atomicMin(&s_fail[n], (int)j);
                 else if (r > 0)
@@ -311,8 +315,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
 
 size_t rs_smem_bytes(uint32_t s, uint32_t sf_per_block) {
     // + 16 alignment slack + 8 so the word gather may read one aligned word past the tile
-    return 4096 + 768 + 256 + NROOTS * 256 + 2 * sizeof(int) * (size_t)sf_per_block + 16 +
-           (size_t)CW * s * sf_per_block + 8;
+    return 2 * sizeof(int) * (size_t)sf_per_block + 16 + (size_t)CW * s * sf_per_block + 8;
 }
 
 uint32_t rs_superframes_per_block(uint32_t s) {
