@@ -145,6 +145,16 @@ bool prepare_pipe(int dev) {
     return true;
 }
 
+// Host-path chunk size (bytes of u8 symbols per pipeline stage); VITERBI_B200_CHUNK_MB overrides the default.
+size_t host_chunk_bytes() {
+    static const size_t bytes = [] {
+        const char* env = getenv("VITERBI_B200_CHUNK_MB");
+        const long mb = (env && *env) ? atol(env) : 8;  // profiles/e2e_chunk_sweep.py: 4-256 MB all within 8 %
+        return (size_t)(mb > 0 ? mb : 8) << 20;
+    }();
+    return bytes;
+}
+
 bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= VITERBI_B200_MAX_FRAMEBITS; }
 
 // Enqueue one batch that is already in device memory.  Scratch is stream-ordered.
@@ -180,9 +190,9 @@ int vit_host(unsigned framebits, const void* syms, bool is_u32, size_t n, uint8_
 
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
     const size_t in_row = nsym * (is_u32 ? 4 : 1);
-    // chunk: about 32 MiB of u8 symbols (a multiple of the 64-frame warp group) so that the H2D copy
+    // chunk: about 8 MiB of u8 symbols (a multiple of the 64-frame warp group) so that the H2D copy
     // of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap on the kPipe streams
-    size_t chunk = ((32u << 20) / nsym) & ~(size_t)63;
+    size_t chunk = (host_chunk_bytes() / nsym) & ~(size_t)63;
     if (chunk < 64) chunk = 64;
     if (chunk > n) chunk = n;
     int rc = FEC_OK;
