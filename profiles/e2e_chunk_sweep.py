@@ -17,7 +17,7 @@ for _ in range(10): vb.lib.viterbi_deconvolve_batch(f, h.data_ptr(), n, o.data_p
 dt = (time.perf_counter() - t0) / 10
 print(round(dt * 1e3, 3), round(n * f / dt / 1e9, 2))
 '''
-for mb in (4, 8, 16, 32, 64, 128, 256):
-    env = dict(os.environ, VITERBI_B200_CHUNK_MB=str(mb))
+for mb in (2048, 4096, 8192, 12288, 16384, 32768, 65536):
+    env = dict(os.environ, VITERBI_B200_CHUNK_FRAMES=str(mb))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
-    print(json.dumps({"chunk_mb": mb, "ms_gbps": out.stdout.strip() or out.stderr[-200:]}), flush=True)
+    print(json.dumps({"chunk_frames": mb, "ms_gbps": out.stdout.strip() or out.stderr[-200:]}), flush=True)

@@ -170,3 +170,40 @@ def test_save_mode_latch(vb):
     # an unsupported frame length is rejected without latching
     rc, _ = vb.deconvolve(7, np.zeros(52, np.uint32))
     assert rc == 1 and vb.lib.fec_in_save_mode() == 0
+
+
+def test_concurrent_callers(vb, checker):
+    """QIRX >= 4.0 calls deconvolve from several threads at once (README.md:56): concurrent drop-in and
+    batched calls must not disturb one another."""
+    import threading
+
+    vb.set_viterbi_kernel(vb.VITERBI_AUTO)
+    frames = {}
+    for tid in range(6):
+        f = (768, 3072, 1536)[tid % 3]
+        sym, _ = dabgen.make_frames(40 + tid, f, 2.5, seed=500 + tid)
+        frames[tid] = (f, sym, checker.deconvolve_batch(f, sym))
+    errors = []
+
+    def worker(tid):
+        f, sym, want = frames[tid]
+        try:
+            for rep in range(4):
+                if tid % 2:
+                    got = vb.deconvolve_batch(f, sym)
+                    if not np.array_equal(got, want):
+                        errors.append((tid, rep, "batch"))
+                else:
+                    for i in range(0, sym.shape[0], 7):
+                        rc, out = vb.deconvolve(f, sym[i].astype(np.uint32))
+                        if rc != 0 or not np.array_equal(out, want[i]):
+                            errors.append((tid, rep, i))
+        except Exception as e:  # pragma: no cover
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in frames]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]

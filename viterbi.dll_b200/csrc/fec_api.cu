@@ -145,14 +145,17 @@ bool prepare_pipe(int dev) {
     return true;
 }
 
-// Host-path chunk size (bytes of u8 symbols per pipeline stage); VITERBI_B200_CHUNK_MB overrides the default.
-size_t host_chunk_bytes() {
-    static const size_t bytes = [] {
-        const char* env = getenv("VITERBI_B200_CHUNK_MB");
-        const long mb = (env && *env) ? atol(env) : 8;  // profiles/e2e_chunk_sweep.py: 4-256 MB all within 8 %
-        return (size_t)(mb > 0 ? mb : 8) << 20;
+// Host-path chunk size in frames per pipeline stage.  The throughput kernel takes a flat ~0.38 us x (F+6)
+// for anything up to ~37,000 frames, the H2D copy of n frames takes n x 4(F+6) B / 55 GB/s, so the
+// kernel hides behind the copy once a chunk holds more than ~5,300 frames whatever F is; 12,288
+// leaves a 2x margin (profiles/e2e_chunk_sweep.py).  VITERBI_B200_CHUNK_FRAMES overrides it.
+size_t host_chunk_frames() {
+    static const size_t frames = [] {
+        const char* env = getenv("VITERBI_B200_CHUNK_FRAMES");
+        const long v = (env && *env) ? atol(env) : 12288;
+        return (size_t)(v >= 64 ? v : 12288) & ~(size_t)63;
     }();
-    return bytes;
+    return frames;
 }
 
 bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= VITERBI_B200_MAX_FRAMEBITS; }
@@ -190,10 +193,9 @@ int vit_host(unsigned framebits, const void* syms, bool is_u32, size_t n, uint8_
 
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
     const size_t in_row = nsym * (is_u32 ? 4 : 1);
-    // chunk: about 8 MiB of u8 symbols (a multiple of the 64-frame warp group) so that the H2D copy
-    // of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap on the kPipe streams
-    size_t chunk = (host_chunk_bytes() / nsym) & ~(size_t)63;
-    if (chunk < 64) chunk = 64;
+    // chunks are pipelined over kPipe streams: the H2D copy of chunk k+1, the kernel of chunk k and the
+    // D2H copy of chunk k-1 overlap
+    size_t chunk = host_chunk_frames();
     if (chunk > n) chunk = n;
     int rc = FEC_OK;
     size_t done = 0;
@@ -418,7 +420,7 @@ int dabplus_decode_superframes(unsigned int framebits, const uint8_t* syms, size
     if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
     const unsigned rsdims = framebits / 192u;
     const size_t nsym = 4 * ((size_t)framebits + 6), in_row = 5 * nsym, out_row = 110 * (size_t)rsdims;
-    size_t chunk = (32u << 20) / in_row;
+    size_t chunk = host_chunk_frames() / 5;
     if (chunk < 1) chunk = 1;
     if (chunk > nsf) chunk = nsf;
     int rc = FEC_OK;
