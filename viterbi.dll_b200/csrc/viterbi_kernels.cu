@@ -21,7 +21,11 @@
 //     scratch area in global memory, fully coalesced (512 B per warp per step).
 //     Shared memory cannot hold them: 8 B x 3078 steps = 24.6 KB per frame would cap an SM at
 //     9 frames.
-//   * traceback runs in the same kernel, by the same thread, reading its own scratch back.
+//   * traceback runs in the same kernel, by the same thread, reading its own scratch back through a
+//     32-step ring of registers (the registers the path metrics no longer need), so that the loads of
+//     28 steps are in flight while the serial state recursion runs.  The position of each decision bit
+//     inside the 64-bit word is free (it is a compile-time constant of the ACS code), so it is chosen
+//     to make that recursion two dependent funnel shifts per step (see dec_word / dec_bit).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -45,6 +49,16 @@ __host__ __device__ constexpr unsigned parity8(unsigned v) {
 __host__ __device__ constexpr unsigned tbit(int i, int k) { return parity8((2u * (unsigned)i) & kPoly(k)); }
 // Branch-metric pattern of butterfly i: bits (T0,T1,T2); T3 == T0 because polys 0 and 3 coincide.
 __host__ __device__ constexpr int pattern(int i) { return (int)(tbit(i, 0) | (tbit(i, 1) << 1) | (tbit(i, 2) << 2)); }
+
+// Where the decision of new state s lives in a frame's 64-bit decision word {lo, hi}.  The traceback
+// keeps the 6-bit state bit-reversed in the low bits of its history register h (newest decoded bit at
+// bit 0), so r = brev6(s).  word = r >> 5 (= s & 1, known one step early), and the bit sits at 31 - (r & 31)
+// so that `word << (h & 31)` brings it to bit 31, ready to be funnel-shifted into h.
+__host__ __device__ constexpr unsigned brev6(unsigned s) {
+    return ((s & 1u) << 5) | ((s & 2u) << 3) | ((s & 4u) << 1) | ((s & 8u) >> 1) | ((s & 16u) >> 3) | ((s & 32u) >> 5);
+}
+__host__ __device__ constexpr int dec_word(int s) { return (int)(brev6((unsigned)s) >> 5); }
+__host__ __device__ constexpr uint32_t dec_bit(int s) { return 1u << (31u - (brev6((unsigned)s) & 31u)); }
 
 constexpr uint32_t kSat = 0x0FF00FF0u;    // 255 * 16 per half: paddusb ceiling
 constexpr uint32_t kM63 = 0x03F003F0u;    // 63 * 16 per half
@@ -117,8 +131,8 @@ __device__ __forceinline__ uint32_t renorm_addend(uint32_t m0) {
 // and symmetrically for 2i+1 (deconvolve.cpp:352-359).
 // kRenorm: the renormalisation that the reference applies after the previous (odd) step is folded
 // into the operand fetch of this step: M' = relu(M + neg), relu(max(M + neg, neg)) == max(M-63*16, 0).
-// Decision words (the reference's decision_t layout, viterbi.h:90-92): x,y = frame A bits 0-31,
-// 32-63; z,w = frame B; bit s = decision of new state s.
+// Decision words: x,y = frame A {lo, hi}; z,w = frame B; the decision of new state s is bit dec_bit(s) of
+// word dec_word(s) (a permutation of the reference's decision_t, viterbi.h:90-92, which is never exported).
 //
 // The file is compiled with ptxas -O1, which keeps this source order, so the loop is software
 // pipelined by hand: the add / add-min stage of butterfly i+1 (2 add-mins + 2 adds) is issued between
@@ -150,19 +164,19 @@ __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)
     }
 #pragma unroll
     for (int i = 0; i < 32; i++) {
-        const int c = i & 1, n = c ^ 1, w = i >> 4;  // new states 2i, 2i+1 live in decision word (2i) / 32
+        const int c = i & 1, n = c ^ 1;
         uint32_t a = 0, b = 0;
         if (i + 1 < 32) {
             a = M[i + 1], b = M[i + 33];
             if (kRenorm) a = __viaddmax_s16x2_relu(a, neg, neg);
         }
-        N[2 * i] = min_decide(t1[c], m0[c], dA[w], dB[w], 1u << ((2 * i) & 31));
+        N[2 * i] = min_decide(t1[c], m0[c], dA[dec_word(2 * i)], dB[dec_word(2 * i)], dec_bit(2 * i));
         if (i + 1 < 32) {
             if (kRenorm) b = __viaddmax_s16x2_relu(b, neg, neg);
             t1[n] = __viaddmin_u16x2(b, bmm[kPat[(i + 1) & 31]], kSat);
             m0[n] = a + bm[kPat[(i + 1) & 31]];
         }
-        N[2 * i + 1] = min_decide(t3[c], m2[c], dA[w], dB[w], 1u << ((2 * i + 1) & 31));
+        N[2 * i + 1] = min_decide(t3[c], m2[c], dA[dec_word(2 * i + 1)], dB[dec_word(2 * i + 1)], dec_bit(2 * i + 1));
         if (i + 1 < 32) {
             t3[n] = __viaddmin_u16x2(b, bm[kPat[(i + 1) & 31]], kSat);
             m2[n] = a + bmm[kPat[(i + 1) & 31]];
@@ -172,84 +186,115 @@ __device__ __forceinline__ uint4 acs_step(const uint32_t (&M)[64], uint32_t (&N)
 }
 
 // ChainBack (deconvolve.cpp:416-435) for the two frames of this thread.
-// The reference keeps state << 2 in an 8-bit register and shifts each decision in at bit 7.  Here
-// the same register is 32 bits wide: h = (h >> 1) | (k << 31), so the state is h >> 26, the
-// reference's byte is h >> 24, and after 32 steps h holds 32 decoded bits (bit 31 = earliest).
-// Per step and frame: pick the decision word by state bit 5 (the sign of h), funnel-shift it by the
-// low 5 state bits, funnel-shift its bit 0 into h -- a 4-instruction dependent chain.
+// The reference keeps state << 2 in an 8-bit register (es = (es >> 1) | (k << 7), state = es >> 2).  Here
+// the history register runs the other way, h = (h << 1) | k: its low six bits are the state bit-reversed,
+// and after 32 steps it holds 32 decoded bits (bit j = time 32m + j).  With the decision layout of
+// dec_word / dec_bit one step is two dependent funnel shifts per frame,
+//     x = word << (h & 31)          the decision bit of the current state arrives at bit 31
+//     h = (h << 1) | (x >> 31)
+// and `word` (lo / hi = bit 5 of the bit-reversed state) is selected during the PREVIOUS step, off the
+// critical path, because bit 5 of the next h is bit 4 of the current one.
 struct TraceState {
-    uint32_t hA = 0, hB = 0;
+    uint32_t hA = 0, hB = 0;  // history registers
+    uint32_t sA = 0, sB = 0;  // decision word already selected for the step about to run
 };
 
-template <bool kWordStores>
-__device__ __forceinline__ void trace_step(TraceState& st, const uint4& w, int t, uint8_t* outA, uint8_t* outB,
-                                           bool liveA, bool liveB) {
-    const uint32_t xA = __funnelshift_r((int32_t)st.hA < 0 ? w.y : w.x, 0u, st.hA >> 26);
-    const uint32_t xB = __funnelshift_r((int32_t)st.hB < 0 ? w.w : w.z, 0u, st.hB >> 26);
-    st.hA = __funnelshift_r(st.hA, xA, 1);
-    st.hB = __funnelshift_r(st.hB, xB, 1);
-    if (kWordStores) {
-        if ((t & 31) == 0) {  // bytes t/8 .. t/8+3, MSB-first within each byte
-            if (liveA) *reinterpret_cast<uint32_t*>(outA + (t >> 3)) = __byte_perm(st.hA, 0u, 0x0123);
-            if (liveB) *reinterpret_cast<uint32_t*>(outB + (t >> 3)) = __byte_perm(st.hB, 0u, 0x0123);
-        }
-    } else if ((t & 7) == 0) {  // the reference stores every step; the store at t % 8 == 0 is the final one
-        if (liveA) outA[t >> 3] = (uint8_t)(st.hA >> 24);
-        if (liveB) outB[t >> 3] = (uint8_t)(st.hB >> 24);
-    }
+// w_next: the decision record of the step that runs after this one (time t - 1).
+__device__ __forceinline__ void trace_step(TraceState& st, const uint4& w_next) {
+    const uint32_t xA = __funnelshift_l(0u, st.sA, st.hA);
+    const uint32_t xB = __funnelshift_l(0u, st.sB, st.hB);
+    st.sA = (st.hA & 16u) ? w_next.y : w_next.x;
+    st.sB = (st.hB & 16u) ? w_next.w : w_next.z;
+    st.hA = __funnelshift_l(xA, st.hA, 1);
+    st.hB = __funnelshift_l(xB, st.hB, 1);
 }
 
-constexpr int kTraceChunk = 12;      // decision words per register buffer (2 buffers in flight)
-constexpr int kTracePrefetch = 96;   // steps ahead that are pulled into L2
+// 32 decoded bits (bit j = time 32m + j) -> 4 output bytes, MSB-first within each byte.
+__device__ __forceinline__ uint32_t trace_word(uint32_t h) { return __byte_perm(__brev(h), 0u, 0x0123); }
 
-__device__ __forceinline__ void trace_load(uint4 (&buf)[kTraceChunk], const uint4* __restrict__ dec, int tb) {
+#ifndef VIT_SYM_PREFETCH
+#define VIT_SYM_PREFETCH 1  // 0: none, 1: L1 prefetch instruction, 2: second register stage
+#endif
+#ifndef VIT_SYM_PREFETCH_PAIRS
+#define VIT_SYM_PREFETCH_PAIRS 6
+#endif
+#ifndef VIT_TRACE_PF_BLOCKS
+#define VIT_TRACE_PF_BLOCKS 4
+#endif
+constexpr uint32_t kSymPrefetchPairs = VIT_SYM_PREFETCH_PAIRS;  // ACS loop: L1 prefetch distance for the symbol rows (8 B pairs)
+constexpr int kTraceRing = 32;      // steps held in registers (one output word)
+constexpr int kTraceSub = 4;        // steps per reload group
+constexpr int kTracePrefetchBlocks = VIT_TRACE_PF_BLOCKS;  // 32-step blocks ahead that are pulled into L2
+
+// Pull the 16 KB decision block starting at `blk` (warp base, lane 0) into L2: 128 lines, 4 per lane.
+__device__ __forceinline__ void trace_prefetch_l2(const uint4* blk, uint32_t lane) {
+    const char* q = reinterpret_cast<const char*>(blk) + lane * 128u;
 #pragma unroll
-    for (int j = 0; j < kTraceChunk; j++) buf[j] = dec[(size_t)(tb + j + 6) * 32];
+    for (int k = 0; k < 4; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + k * 4096));
 }
 
-// Each lane prefetches its own 16 bytes; the 32 lanes together touch the 4 lines of one step.
-__device__ __forceinline__ void trace_prefetch_l2(const uint4* __restrict__ dec, int tb) {
-    if (tb < 0) return;
-#pragma unroll
-    for (int j = 0; j < kTraceChunk; j++)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(dec + (size_t)(tb + j + 6) * 32));
-}
-
+// The state recursion is serial, but the decision records it consumes do not depend on it.  They were
+// written by this same thread and have mostly been evicted to HBM by now, so they come back in two
+// stages: an L2 prefetch kTracePrefetchBlocks blocks ahead, and a ring of kTraceRing records in registers
+// (the registers the path metrics no longer need): as soon as a group of kTraceSub records has been
+// consumed it is reloaded with the records of the next block, 28 steps before they are needed.
 template <bool kWordStores>
-__device__ __forceinline__ void trace_chunk(TraceState& st, const uint4 (&buf)[kTraceChunk], int tb, uint8_t* outA,
-                                            uint8_t* outB, bool liveA, bool liveB) {
-#pragma unroll
-    for (int j = kTraceChunk - 1; j >= 0; j--) trace_step<kWordStores>(st, buf[j], tb + j, outA, outB, liveA, liveB);
-}
-
-// The state recursion is serial, but the decision words it consumes do not depend on it.  They were
-// written by this same thread and have mostly been evicted to HBM by now, so they are pulled back in
-// two stages: an L2 prefetch kTracePrefetch steps ahead, and register double-buffering one chunk
-// ahead (in the registers the path metrics no longer need).  The traceback then runs at ALU latency
-// instead of one memory round trip per chunk.
-template <bool kWordStores>
-__device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_t framebits, uint8_t* outA,
-                                          uint8_t* outB, bool liveA, bool liveB) {
+__device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_t lane, uint32_t framebits,
+                                          uint8_t* outA, uint8_t* outB, bool liveA, bool liveB) {
+    constexpr int kBlk = kTraceRing * 32;  // uint4 elements per 32-step block of one warp
     TraceState st;
+    const int nblk = (int)(framebits / kTraceRing);
     int t = (int)framebits - 1;
-    const int head = (int)(framebits % kTraceChunk);
-    int tb = t - head + 1 - kTraceChunk;  // base of the first full chunk (a multiple of kTraceChunk)
-    for (int d = 0; d < kTracePrefetch; d += kTraceChunk) trace_prefetch_l2(dec, tb - d);
-    for (int i = 0; i < head; i++, t--) trace_step<kWordStores>(st, dec[(size_t)(t + 6) * 32], t, outA, outB, liveA, liveB);
-    if (tb < 0) return;
-    uint4 bufA[kTraceChunk], bufB[kTraceChunk];
-    trace_load(bufA, dec, tb);
-    while (true) {
-        trace_prefetch_l2(dec, tb - kTracePrefetch);
-        if (tb >= kTraceChunk) trace_load(bufB, dec, tb - kTraceChunk);
-        trace_chunk<kWordStores>(st, bufA, tb, outA, outB, liveA, liveB);
-        tb -= kTraceChunk;
-        if (tb < 0) break;
-        trace_prefetch_l2(dec, tb - kTracePrefetch);
-        if (tb >= kTraceChunk) trace_load(bufA, dec, tb - kTraceChunk);
-        trace_chunk<kWordStores>(st, bufB, tb, outA, outB, liveA, liveB);
-        tb -= kTraceChunk;
-        if (tb < 0) break;
+    // record of time 32 (nblk - 1), this lane
+    const uint4* p = dec + (size_t)((nblk > 0 ? nblk - 1 : 0) * kTraceRing + 6) * 32;
+    for (int d = 1; d < kTracePrefetchBlocks; d++)
+        if (nblk - 1 - d >= 0) trace_prefetch_l2(p - lane - (size_t)d * kBlk, lane);
+    uint4 R[kTraceRing];
+    if (nblk > 0) {
+#pragma unroll
+        for (int j = 0; j < kTraceRing; j++) R[j] = p[j * 32];
+    } else {  // defined on every path: an undefined ring would be live across the whole kernel for ptxas
+#pragma unroll
+        for (int j = 0; j < kTraceRing; j++) R[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (kWordStores) {  // start state 0: word lo of the last record
+        st.sA = R[kTraceRing - 1].x, st.sB = R[kTraceRing - 1].z;
+    } else {
+        const uint4 w = dec[(size_t)(t + 6) * 32];
+        st.sA = w.x, st.sB = w.z;
+    }
+    if (!kWordStores) {  // ragged top: framebits % 32 steps, then the partial output word byte by byte
+        const int head = (int)(framebits % kTraceRing);
+        for (int i = 0; i < head; i++, t--) trace_step(st, dec[(size_t)(t > 0 ? t + 5 : 6) * 32]);
+        const uint32_t vA = __brev(st.hA), vB = __brev(st.hB);
+        for (int b = 0; b < (head + 7) / 8; b++) {
+            if (liveA) outA[nblk * 4 + b] = (uint8_t)(vA >> (24 - 8 * b));
+            if (liveB) outB[nblk * 4 + b] = (uint8_t)(vB >> (24 - 8 * b));
+        }
+    }
+    for (int m = nblk - 1; m >= 0; m--) {
+        const uint4* pn = m > 0 ? p - kBlk : p;  // last block: reload in place (values unused)
+        if (m >= kTracePrefetchBlocks) trace_prefetch_l2(p - lane - (size_t)kTracePrefetchBlocks * kBlk, lane);
+#pragma unroll
+        for (int j = kTraceRing - 1; j >= 0; j--) {
+            trace_step(st, R[j > 0 ? j - 1 : kTraceRing - 1]);  // at j == 0 R[31] already holds the next block
+            if (j % kTraceSub == 0) {
+#pragma unroll
+                for (int k = 0; k < kTraceSub; k++) R[j + k] = pn[(j + k) * 32];
+            }
+        }
+        if (kWordStores) {
+            if (liveA) *reinterpret_cast<uint32_t*>(outA + 4 * m) = trace_word(st.hA);
+            if (liveB) *reinterpret_cast<uint32_t*>(outB + 4 * m) = trace_word(st.hB);
+        } else {
+            const uint32_t vA = __brev(st.hA), vB = __brev(st.hB);
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (liveA) outA[4 * m + b] = (uint8_t)(vA >> (24 - 8 * b));
+                if (liveB) outB[4 * m + b] = (uint8_t)(vB >> (24 - 8 * b));
+            }
+        }
+        p = pn;
     }
 }
 
@@ -285,21 +330,45 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
 
         // Two steps per iteration (the reference's Butterfly256 granularity): even step X -> Y with the
         // pending renormalisation folded in, odd step Y -> X, then the renormalisation test on the new
-        // metric of state 0.  The 8 symbol bytes of the next iteration are fetched while this one runs.
+        // metric of state 0.  The 8 symbol bytes of the next iteration are fetched while this one runs; every
+        // fourth such load starts a new 32-byte sector, and one iteration of lead did not cover an L2 / HBM
+        // round trip (ncu: 9 % of the loop's samples waited on it), so the sector kSymPrefetchPairs
+        // iterations ahead is prefetched into L1 (no registers: the loop body has none to spare).
         // (A 6-step body would make the register renaming of the butterfly network close on itself
         // and save ~30 moves per step, but it overflows the instruction cache once warps are in
         // different phases: measured 94 vs 118 Gbit/s on the MSC batch.)
         uint32_t neg = 0u;
-        uint2 a0 = __ldg(rowA), b0 = __ldg(rowB);  // steps >= 6: the first pair always exists
+        uint2 a0 = __ldg(rowA), b0 = __ldg(rowB);  // steps >= 8: the first pairs always exist
+#if VIT_SYM_PREFETCH == 2
+        uint2 a1 = __ldg(rowA + 1), b1 = __ldg(rowB + 1);
+#endif
+        const uint32_t last_pair = steps / 2 - 1;
         for (uint32_t t = 0; t < steps; t += 2) {
+#if VIT_SYM_PREFETCH == 2
+            uint2 a2 = a1, b2 = b1;
+            if (t + 4 < steps) a2 = __ldg(rowA + (t >> 1) + 2), b2 = __ldg(rowB + (t >> 1) + 2);
+#else
             uint2 na0 = a0, nb0 = b0;
             if (t + 2 < steps) na0 = __ldg(rowA + (t >> 1) + 1), nb0 = __ldg(rowB + (t >> 1) + 1);
+#endif
+#if VIT_SYM_PREFETCH == 1
+            {
+                const uint32_t ahead = min((t >> 1) + kSymPrefetchPairs, last_pair);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rowA + ahead));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rowB + ahead));
+            }
+#endif
             dec[(size_t)(t + 0) * 32] = acs_step<true>(X, Y, a0.x, b0.x, neg);
             dec[(size_t)(t + 1) * 32] = acs_step<false>(Y, X, a0.y, b0.y, 0u);
             neg = renorm_addend(X[0]);
+#if VIT_SYM_PREFETCH == 2
+            a0 = a1, b0 = b1, a1 = a2, b1 = b2;
+#else
             a0 = na0, b0 = nb0;
+#endif
         }
-        traceback<kWordStores>(dec, framebits, out + fA * outbytes, out + fB * outbytes, liveA, liveB);
+        (void)last_pair;
+        traceback<kWordStores>(dec, lane, framebits, out + fA * outbytes, out + fB * outbytes, liveA, liveB);
 
         unsigned long long next = 0;
         if (lane == 0) next = nwarps + atomicAdd(ticket, 1ull);
