@@ -103,6 +103,23 @@ def test_partial_write_rule_keeps_caller_bytes(vb, checker):
     assert (want_ret == -1).any() and (want_ret >= 0).any()
 
 
+@pytest.mark.parametrize("s", [1, 3, 8, 16])
+def test_pinned_host_buffers(vb, checker, s):
+    """Pinned caller buffers (fec_host_alloc) through the host-pointer call: same bytes, same partial-write
+    rule (rschecksf.cpp:80-88), the caller's fill pattern kept where the reference keeps it."""
+    n = 3000 + s
+    rx, _, _ = dabgen.make_superframes(n, s, seed=40 + s)
+    want_out, want_ret = checker.rs_batch(rx, s, fill=0xA5)
+    pin_rx = vb.host_array(rx.shape)
+    pin_rx[:] = rx
+    pin_out = vb.host_array((n, 110 * s))
+    pin_out[:] = 0xA5
+    out, ret = vb.rs_check_superframe_batch(pin_rx, s, out=pin_out)
+    assert out is pin_out
+    assert np.array_equal(ret, want_ret) and np.array_equal(pin_out, want_out)
+    assert (want_ret < 0).any() and (want_ret >= 0).any()  # both write paths were exercised
+
+
 def test_one_million_superframes_bit_exact(vb, checker):
     """BASELINE config 4: 10^6 superframes, s = 1..8, 0-7 byte errors per codeword."""
     per_s = 125000 if checker.kind == "reference" else 8000

@@ -144,6 +144,24 @@ def rs_check_superframe_batch(rx: np.ndarray, RSDims: int, out: np.ndarray | Non
     return out, ret
 
 
+def host_array(shape, dtype=np.uint8) -> np.ndarray:
+    """Pinned host array from fec_host_alloc (freed with the array): host-pointer calls run at PCIe speed on
+    pinned buffers (pageable ones go through the driver's bounce buffers)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib.fec_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise FecError("fec_host_alloc failed: %s" % (lib.fec_last_error() or b"").decode())
+
+    class _Owner:
+        def __del__(self, _free=lib.fec_host_free, _p=ptr):
+            _free(_p)
+
+    buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(ptr)
+    buf._owner = _Owner()  # the ctypes buffer keeps the allocation alive; numpy keeps the buffer
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 # -------------------------------------------------------------------------------------------
 # batched, device buffers (torch tensors are only used as handles to HBM and streams)
 # -------------------------------------------------------------------------------------------
