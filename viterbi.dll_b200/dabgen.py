@@ -91,11 +91,11 @@ def lcg_symbols(seed: int, count: int) -> np.ndarray:
 # torch generators (device-side synthetic input for the large benchmark configs)
 # ---------------------------------------------------------------------------
 def make_frames_torch(n: int, framebits: int, ebn0_db: float, seed: int, device, chunk: int = 8192,
-                      want_bits: bool = False):
+                      want_bits: bool = False, payload=None):
     """Same channel model generated with torch on `device` -> u8 tensor [n, 4*(F+6)].
 
     Used only to manufacture benchmark inputs already resident in HBM; returns
-    (symbols, packed_bits or None).
+    (symbols, packed_bits or None).  `payload` (u8 tensor [n, F/8], MSB-first) replaces the random info bits.
     """
     import torch
 
@@ -106,9 +106,14 @@ def make_frames_torch(n: int, framebits: int, ebn0_db: float, seed: int, device,
     syms = torch.empty((n, steps * RATE), dtype=torch.uint8, device=device)
     packed = torch.empty((n, nout(framebits)), dtype=torch.uint8, device=device) if want_bits else None
     weights = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=device)
+    shifts = torch.tensor([7, 6, 5, 4, 3, 2, 1, 0], dtype=torch.uint8, device=device)
     for lo in range(0, n, chunk):
         m = min(chunk, n - lo)
-        bits = torch.randint(0, 2, (m, framebits), generator=g, device=device, dtype=torch.uint8)
+        if payload is None:
+            bits = torch.randint(0, 2, (m, framebits), generator=g, device=device, dtype=torch.uint8)
+        else:
+            pb = payload[lo : lo + m].to(device)
+            bits = ((pb[:, :, None] >> shifts) & 1).reshape(m, framebits)
         padded = torch.zeros((m, framebits + 2 * (K - 1)), dtype=torch.uint8, device=device)
         padded[:, K - 1 : K - 1 + framebits] = bits
         code = torch.empty((m, steps, RATE), dtype=torch.uint8, device=device)
@@ -217,13 +222,15 @@ def make_superframes(n: int, s: int, seed: int, max_err: int = 7):
     return rs_interleave(rx, s), payload, nerr.reshape(n, s)
 
 
-def make_superframes_torch(n: int, s: int, seed: int, device, max_err: int = 7, chunk: int = 1 << 18):
+def make_superframes_torch(n: int, s: int, seed: int, device, max_err: int = 7, chunk: int = 1 << 18,
+                           want_payload: bool = False):
     """Device-side version of make_superframes (benchmark inputs): -> (received [n,120*s] u8 tensor,
-    errors per codeword [n,s])."""
+    errors per codeword [n,s]) and, with want_payload, the clean payload [n,110*s]."""
     import torch
 
     g = torch.Generator(device=device)
     g.manual_seed(seed)
+    msgs = torch.empty((n * s, RS_K), dtype=torch.uint8, device=device) if want_payload else None
     exp = torch.from_numpy(_EXP.astype(np.int64)).to(device)
     log = torch.from_numpy(_LOG.astype(np.int64)).to(device)
     ghi_log = log[torch.from_numpy(_GEN[RS_T2 - 1 :: -1].astype(np.int64)).to(device)]  # g_9..g_0 (all non-zero)
@@ -246,7 +253,11 @@ def make_superframes_torch(n: int, s: int, seed: int, device, max_err: int = 7, 
         cw ^= torch.where(order < nerr[:, None], vals, torch.zeros_like(vals))
         rx[lo : lo + m] = cw.to(torch.uint8)
         nerr_all[lo : lo + m] = nerr
+        if want_payload:
+            msgs[lo : lo + m] = msg.to(torch.uint8)
     rx = rx.reshape(n, s, RS_N).transpose(1, 2).contiguous().reshape(n, RS_N * s)
+    if want_payload:
+        return rx, nerr_all.reshape(n, s), msgs.reshape(n, s, RS_K).transpose(1, 2).contiguous().reshape(n, RS_K * s)
     return rx, nerr_all.reshape(n, s)
 
 
@@ -272,3 +283,14 @@ def make_superframe_frames(nsf: int, framebits: int, ebn0_db: float, seed: int, 
     syms = soft_symbols(conv_encode(bits), ebn0_db, rng)
     payload = np.ascontiguousarray(msg.reshape(nsf, s, RS_K).transpose(0, 2, 1)).reshape(nsf, RS_K * s)
     return syms, payload, sf
+
+
+def make_superframe_frames_torch(nsf: int, framebits: int, ebn0_db: float, seed: int, device, max_err: int = 0):
+    """Device-side version of make_superframe_frames (benchmark inputs for the end-to-end configuration):
+    -> (symbols u8 [nsf*5, 4*(F+6)], clean payload u8 [nsf, 110*s])."""
+    if framebits % 192:
+        raise ValueError("framebits must be a multiple of 192")
+    s = framebits // 192
+    sf, _, payload = make_superframes_torch(nsf, s, seed, device, max_err=max_err, want_payload=True)
+    syms, _ = make_frames_torch(nsf * 5, framebits, ebn0_db, seed + 1, device, payload=sf.reshape(nsf * 5, framebits // 8))
+    return syms, payload
