@@ -65,7 +65,7 @@ def main():
     total_sf = args.total_frames // 5
     lo, hi = sharding.shard_bounds(total_sf, world, rank)  # superframes of this rank
     my_sf = hi - lo
-    res_sf = min(my_sf, args.resident_frames // 5)
+    res_sf = min(my_sf, -(-args.resident_frames // 5))
     passes = (my_sf + res_sf - 1) // res_sf
     last_sf = my_sf - (passes - 1) * res_sf  # superframes of the final (possibly shorter) pass
 
