@@ -84,6 +84,20 @@ int viterbi_deconvolve_batch_device(unsigned int framebits, const uint8_t* d_sym
 int viterbi_deconvolve_batch_u32_device(unsigned int framebits, const uint32_t* d_syms, size_t n,
                                         uint8_t* d_out, void* stream);
 
+/* Depuncturing front end (the step a receiver performs immediately before
+ * deconvolve(), outside viterbi.dll): rx [n][rx_per_frame] holds only the soft symbols that were transmitted;
+ * keep [4*(F+6)] (host memory, one byte per mother-code symbol, non-zero = transmitted) is the puncturing
+ * pattern of a whole frame, the same for every frame of the batch; punctured positions are filled with
+ * `erasure` (0..255, normally the midpoint 128) on the device and the result is decoded exactly like
+ * viterbi_deconvolve_batch() would decode the expanded symbols.  The number of non-zero bytes in keep must
+ * equal rx_per_frame.  Up to 4x fewer bytes cross PCIe than with the expanded layout. */
+int viterbi_deconvolve_batch_punctured(unsigned int framebits, const uint8_t* rx, size_t rx_per_frame,
+                                       const uint8_t* keep, unsigned int erasure, size_t n, uint8_t* out);
+/* d_rx / d_out in HBM, keep still a host pointer (it is turned into an index table and uploaded on `stream`). */
+int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint8_t* d_rx, size_t rx_per_frame,
+                                              const uint8_t* keep, unsigned int erasure, size_t n, uint8_t* d_out,
+                                              void* stream);
+
 /* n superframes with the same RSDims: in [n][120*RSDims], out [n][110*RSDims], ret [n].
  * Per superframe identical to RScheckSuperframe(), including the partial-write rule: bytes of out
  * belonging to the first failing column and later ones are not written. */

@@ -49,3 +49,28 @@ for f in (768, 3072):
             assert rc == 0
         print(json.dumps({"framebits": f, "dropin_deconvolve_us": round((time.perf_counter() - t0) / 50 * 1e6, 1), "kernel": name}), flush=True)
 vb.set_viterbi_kernel(vb.VITERBI_AUTO)
+
+# concurrent drop-in callers (README.md:56: QIRX >= 4.0 calls deconvolve from several threads): each thread has
+# its own streams and staging buffers, so single-frame calls overlap on the device.  ctypes releases the GIL.
+import threading  # noqa: E402
+
+for f in (768, 3072):
+    sym1, _ = dabgen.make_frames(1, f, 3.0, seed=2)
+    for nthreads in (1, 2, 4, 8):
+        calls = 200
+
+        def worker():
+            s32 = sym1[0].astype(np.uint32)
+            o = np.zeros(f // 8, np.uint8)
+            for _ in range(calls):
+                assert vb.lib.deconvolve(f, s32.ctypes.data, 0, o.ctypes.data) == 0
+
+        worker_threads = [threading.Thread(target=worker) for _ in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in worker_threads:
+            t.start()
+        for t in worker_threads:
+            t.join()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"framebits": f, "threads": nthreads, "dropin_calls_per_s": round(nthreads * calls / dt, 1),
+                          "us_per_call_per_thread": round(dt / calls * 1e6, 1)}), flush=True)

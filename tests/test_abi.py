@@ -80,5 +80,37 @@ def test_argument_validation(vb):
     assert vb.lib.viterbi_deconvolve_batch(768, None, 0, None) == vb.FEC_OK  # empty batch is a no-op
     assert vb.lib.rs_check_superframe_batch(None, 0, 1, None, None) == vb.FEC_ERR_ARG
     assert vb.lib.rs_check_superframe_batch(None, 4, 0, None, None) == vb.FEC_OK
+    # punctured input: the keep pattern must account for exactly rx_per_frame symbols (checked before any device use)
+    keep = np.ones(4 * 14, dtype=np.uint8)
+    kp, zp = keep.ctypes.data_as(ctypes.c_void_p), z.ctypes.data_as(ctypes.c_void_p)
+    assert vb.lib.viterbi_deconvolve_batch_punctured(8, zp, 55, kp, 128, 1, zp) == vb.FEC_ERR_ARG
+    assert vb.lib.viterbi_deconvolve_batch_punctured(8, zp, 56, kp, 300, 1, zp) == vb.FEC_ERR_ARG
+    assert vb.lib.viterbi_deconvolve_batch_punctured(8, zp, 56, None, 128, 1, zp) == vb.FEC_ERR_ARG
+    assert vb.lib.viterbi_deconvolve_batch_punctured(8, None, 56, kp, 128, 0, None) == vb.FEC_OK
     assert vb.lib.GetCPUCaps() == 0
     vb.lib.WakeUpYMM()
+
+
+def test_call_log_is_env_gated(vb, tmp_path):
+    """VITERBI_B200_LOG=<file> (read by initialize()) logs one line per API call, like the reference's
+    VIT_WRITE_LOGFILE build (deconvolve.cpp:602-621); off by default.  Works without a device: failed calls
+    are logged with their return value."""
+    import os
+
+    path = tmp_path / "calls.log"
+    os.environ["VITERBI_B200_LOG"] = str(path)
+    try:
+        vb.initialize()
+        vb.deconvolve(7, np.zeros(52, np.uint32))  # unsupported framebits: rc 1, no save mode
+        out = np.zeros(110, dtype=np.uint8)
+        vb.RScheckSuperframe(np.zeros(120, dtype=np.uint8), 0, 1, out)
+    finally:
+        del os.environ["VITERBI_B200_LOG"]
+        vb.initialize()
+    lines = path.read_text().splitlines()
+    assert len(lines) == 2
+    assert " deco:" in lines[0] and "rc: 1" in lines[0] and "shape:    7" in lines[0]
+    assert " rssf:" in lines[1] and "dT:" in lines[1] and "TID:" in lines[1] and "ReE: 0" in lines[1]
+    n = len(lines)
+    vb.deconvolve(7, np.zeros(52, np.uint32))  # logging is off again
+    assert len(path.read_text().splitlines()) == n

@@ -96,6 +96,46 @@ def test_out_of_range_symbols_low_byte_only(vb, kernel, checker):
     assert rc == 0 and np.array_equal(out, want[3])
 
 
+@pytest.mark.parametrize("framebits,n,ebn0", [(768, 700, 4.0), (768, 5000, 5.0), (3072, 300, 4.0), (96, 130, 6.0)])
+def test_punctured_input_equals_reference_on_expanded_symbols(vb, kernel, checker, framebits, n, ebn0):
+    """Depuncturing front end: decoding the transmitted symbols + keep pattern must equal the
+    reference decoder run on the host-expanded rate-1/4 stream (erasures = 128), host and device flavours."""
+    import torch
+
+    rng = np.random.default_rng(framebits + n)
+    sym, _ = dabgen.make_frames(n, framebits, ebn0, seed=framebits + 3 * n)
+    patterns = [dabgen.fic_puncture_pattern()] if framebits == 768 else []
+    patterns.append(dabgen.puncture_pattern(framebits, [(framebits // 32, 8)]))          # rate 1/2 everywhere
+    patterns.append((rng.random(4 * (framebits + 6)) < 0.6).astype(np.uint8))           # arbitrary pattern
+    patterns.append(np.ones(4 * (framebits + 6), np.uint8))                             # nothing punctured
+    for keep in patterns:
+        rx = dabgen.puncture(sym, keep)
+        for erasure in (128, 0):
+            want = checker.deconvolve_batch(framebits, dabgen.depuncture(rx, keep, erasure))
+            assert np.array_equal(vb.deconvolve_batch_punctured(framebits, rx, keep, erasure), want)
+            got = vb.deconvolve_batch_punctured_device(framebits, torch.from_numpy(rx).cuda(), keep, erasure)
+            assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_punctured_fic_recovers_payload(vb):
+    """FIC-shaped puncturing (3096 -> 2304 symbols) at a comfortable Eb/N0: the payload comes back."""
+    sym, bits = dabgen.make_frames(4096, 768, 7.0, seed=9)
+    keep = dabgen.fic_puncture_pattern()
+    assert keep.sum() == 2304
+    out = vb.deconvolve_batch_punctured(768, dabgen.puncture(sym, keep), keep)
+    assert (out != bits).any(axis=1).mean() < 0.01
+
+
+def test_punctured_argument_checks(vb):
+    keep = dabgen.fic_puncture_pattern()
+    rx = np.zeros((3, 2304), np.uint8)
+    with pytest.raises(vb.FecError):
+        vb.deconvolve_batch_punctured(768, rx[:, :-1], keep)  # pattern keeps 2304, rows hold 2303
+    with pytest.raises(vb.FecError):
+        vb.deconvolve_batch_punctured(768, rx, keep, erasure=256)
+    assert vb.lib.fec_in_save_mode() == 0
+
+
 def test_empty_and_zero_length(vb):
     assert vb.deconvolve_batch(768, np.zeros((0, 3096), np.uint8)).shape == (0, 96)
     assert vb.deconvolve_batch(0, np.zeros((5, 24), np.uint8)).shape == (5, 0)  # F = 0: nothing to write

@@ -40,6 +40,10 @@ _SIGNATURES = {
     "viterbi_deconvolve_batch_u32": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp]),
     "viterbi_deconvolve_batch_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
     "viterbi_deconvolve_batch_u32_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
+    "viterbi_deconvolve_batch_punctured": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, ctypes.c_uint,
+                                                            ctypes.c_size_t, _vp]),
+    "viterbi_deconvolve_batch_punctured_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, ctypes.c_uint,
+                                                                   ctypes.c_size_t, _vp, _vp]),
     "rs_check_superframe_batch": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp]),
     "rs_check_superframe_batch_device": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp, _vp]),
     "dabplus_decode_superframes": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
@@ -133,6 +137,21 @@ def deconvolve_batch(framebits: int, syms: np.ndarray, out: np.ndarray | None = 
     return out
 
 
+def deconvolve_batch_punctured(framebits: int, rx: np.ndarray, keep: np.ndarray, erasure: int = 128,
+                               out: np.ndarray | None = None) -> np.ndarray:
+    """rx [n, kept] uint8 = the transmitted soft symbols only; keep [4*(F+6)] non-zero where transmitted."""
+    rx = np.ascontiguousarray(rx, dtype=np.uint8)
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    if keep.shape != (4 * (framebits + 6),):
+        raise ValueError("keep must be [4*(framebits+6)]")
+    n = rx.shape[0]
+    if out is None:
+        out = np.zeros((n, (framebits + 7) // 8), dtype=np.uint8)
+    _check(lib.viterbi_deconvolve_batch_punctured(framebits, _ptr(rx), rx.shape[1], _ptr(keep), erasure, n, _ptr(out)),
+           "viterbi_deconvolve_batch_punctured")
+    return out
+
+
 def rs_check_superframe_batch(rx: np.ndarray, RSDims: int, out: np.ndarray | None = None, fill: int = 0):
     """rx [n, 120*s] -> (out [n, 110*s], ret [n] int32).  `out` is updated in place when given."""
     rx = np.ascontiguousarray(rx, dtype=np.uint8)
@@ -187,6 +206,21 @@ def deconvolve_batch_device(framebits: int, syms, out=None, stream=None):
         assert syms.element_size() == 4
         rc = lib.viterbi_deconvolve_batch_u32_device(framebits, syms.data_ptr(), n, out.data_ptr(), _stream_ptr(stream))
     _check(rc, "viterbi_deconvolve_batch_device")
+    return out
+
+
+def deconvolve_batch_punctured_device(framebits: int, rx, keep: np.ndarray, erasure: int = 128, out=None, stream=None):
+    """rx: CUDA uint8 tensor [n, kept]; keep: host array [4*(F+6)].  Asynchronous on `stream`."""
+    import torch
+
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    n = rx.shape[0]
+    if out is None:
+        out = torch.empty((n, (framebits + 7) // 8), dtype=torch.uint8, device=rx.device)
+    assert rx.is_contiguous() and out.is_contiguous() and keep.shape == (4 * (framebits + 6),)
+    rc = lib.viterbi_deconvolve_batch_punctured_device(framebits, rx.data_ptr(), rx.shape[1], _ptr(keep), erasure, n,
+                                                       out.data_ptr(), _stream_ptr(stream))
+    _check(rc, "viterbi_deconvolve_batch_punctured_device")
     return out
 
 

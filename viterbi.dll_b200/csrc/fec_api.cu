@@ -7,11 +7,15 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/viterbi_b200.h"
 #include "fec_internal.h"
@@ -47,12 +51,17 @@ struct Slot {
     size_t in_cap = 0, out_cap = 0, aux_cap = 0, scratch_cap = 0, pin_cap = 0;
 };
 
+// Staging state of the host-pointer calls.  One per calling thread: QIRX >= 4.0 calls deconvolve() from several
+// threads at once (README.md:56), and with per-thread streams and buffers those calls overlap on the device
+// instead of queueing behind one lock.  Released when the thread exits.
 struct HostPipe {
-    std::mutex mu;
     int device = -1;
     Slot slot[kPipe];
+    void* d_idx = nullptr;  // depuncturing index table of the call in progress
+    size_t idx_cap = 0;
+    ~HostPipe();
 };
-HostPipe g_pipe;
+thread_local HostPipe g_pipe;
 
 bool fail(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return false;
@@ -117,8 +126,8 @@ bool grow(void** p, size_t* cap, size_t need, bool pinned = false) {
     return true;
 }
 
-void release_pipe() {
-    for (Slot& s : g_pipe.slot) {
+void release_pipe(HostPipe& pipe) {
+    for (Slot& s : pipe.slot) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
         if (s.d_aux) cudaFree(s.d_aux);
@@ -127,15 +136,22 @@ void release_pipe() {
         if (s.stream) cudaStreamDestroy(s.stream);
         s = Slot();
     }
-    g_pipe.device = -1;
+    if (pipe.d_idx) cudaFree(pipe.d_idx);
+    pipe.d_idx = nullptr;
+    pipe.idx_cap = 0;
+    pipe.device = -1;
+    (void)cudaGetLastError();  // a thread that outlives the CUDA context frees nothing; that is fine
 }
 
-// g_pipe.mu must be held
+HostPipe::~HostPipe() {
+    if (device >= 0 && cudaSetDevice(device) == cudaSuccess) release_pipe(*this);
+}
+
 bool prepare_pipe(int dev) {
     if (g_pipe.device != dev) {
         if (g_pipe.device >= 0) {
             cudaSetDevice(g_pipe.device);
-            release_pipe();
+            release_pipe(g_pipe);
             cudaSetDevice(dev);
         }
         g_pipe.device = dev;
@@ -180,19 +196,41 @@ int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_
     return fail(e, "viterbi kernel launch") ? FEC_ERR_DEVICE : FEC_OK;
 }
 
+enum class SymFormat { U8, U32, Punctured };
+
+// keep[4*(F+6)] (non-zero = transmitted) -> idx[p] = position of mother-code symbol p in a received row, -1 if
+// punctured.  Returns false when the pattern does not account for exactly rx_per_frame symbols.
+bool puncture_index(unsigned framebits, const uint8_t* keep, size_t rx_per_frame, std::vector<int32_t>& idx) {
+    const size_t nsym = 4 * ((size_t)framebits + 6);
+    idx.resize(nsym);
+    int32_t next = 0;
+    for (size_t p = 0; p < nsym; p++) idx[p] = keep[p] ? next++ : -1;
+    return (size_t)next == rx_per_frame;
+}
+
 // Host-pointer batch: chunks pipelined over kPipe streams (H2D | kernel | D2H overlap).
-int vit_host(unsigned framebits, const void* syms, bool is_u32, size_t n, uint8_t* out) {
+int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint8_t* out, const uint8_t* keep = nullptr,
+             size_t rx_per_frame = 0, unsigned erasure = 0) {
     if (!vit_args_ok(framebits)) return bad_arg("framebits must be even and <= 9216");
     if (n == 0 || framebits == 0) return FEC_OK;
     if (!syms || !out) return bad_arg("null pointer");
+    const bool is_u32 = fmt == SymFormat::U32, punct = fmt == SymFormat::Punctured;
+    std::vector<int32_t> idx;
+    if (punct) {
+        if (!keep) return bad_arg("null pointer");
+        if (erasure > 255) return bad_arg("erasure must be 0..255");
+        if (!puncture_index(framebits, keep, rx_per_frame, idx)) return bad_arg("keep pattern does not match rx_per_frame");
+    }
     int dev;
     DeviceState* st = device_state(&dev);
     if (!st) return FEC_ERR_DEVICE;
-    std::lock_guard<std::mutex> lock(g_pipe.mu);
     if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
 
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
-    const size_t in_row = nsym * (is_u32 ? 4 : 1);
+    const size_t in_row = punct ? rx_per_frame : nsym * (is_u32 ? 4 : 1);
+    if (punct && (!grow(&g_pipe.d_idx, &g_pipe.idx_cap, nsym * sizeof(int32_t)) ||
+                  fail(cudaMemcpy(g_pipe.d_idx, idx.data(), nsym * sizeof(int32_t), cudaMemcpyHostToDevice), "H2D index table")))
+        return FEC_ERR_DEVICE;
     // chunks are pipelined over kPipe streams: the H2D copy of chunk k+1, the kernel of chunk k and the
     // D2H copy of chunk k-1 overlap
     size_t chunk = host_chunk_frames();
@@ -207,12 +245,23 @@ int vit_host(unsigned framebits, const void* syms, bool is_u32, size_t n, uint8_
         const int blocks = viterbi_grid_blocks(st->num_sms, m);
         if (!grow(&s.d_in, &s.in_cap, m * nsym) || !grow(&s.d_out, &s.out_cap, m * nout) ||
             !grow(&s.d_scratch, &s.scratch_cap, viterbi_scratch_bytes(blocks, framebits)) ||
-            (is_u32 && !grow(&s.d_aux, &s.aux_cap, m * in_row))) {
+            ((is_u32 || punct) && !grow(&s.d_aux, &s.aux_cap, m * in_row + 16))) {
             rc = FEC_ERR_DEVICE;
             break;
         }
         const uint8_t* src = (const uint8_t*)syms + done * in_row;
-        if (is_u32) {
+        if (punct) {
+            if (in_row && fail(cudaMemcpyAsync(s.d_aux, src, m * in_row, cudaMemcpyHostToDevice, s.stream), "H2D")) {
+                rc = FEC_ERR_DEVICE;
+                break;
+            }
+            if (fail(launch_depuncture((const uint8_t*)s.d_aux, rx_per_frame, (const int32_t*)g_pipe.d_idx, framebits, erasure,
+                                       (uint8_t*)s.d_in, m, st->num_sms, s.stream),
+                     "depuncture kernel")) {
+                rc = FEC_ERR_DEVICE;
+                break;
+            }
+        } else if (is_u32) {
             if (fail(cudaMemcpyAsync(s.d_aux, src, m * in_row, cudaMemcpyHostToDevice, s.stream), "H2D") ||
                 fail(launch_compact_symbols((const uint32_t*)s.d_aux, (uint8_t*)s.d_in, m * nsym, st->num_sms, s.stream),
                      "compact kernel")) {
@@ -243,7 +292,6 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
     int dev;
     DeviceState* st = device_state(&dev);
     if (!st) return FEC_ERR_DEVICE;
-    std::lock_guard<std::mutex> lock(g_pipe.mu);
     if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
     const size_t in_row = 120 * (size_t)s, out_row = 110 * (size_t)s;
     size_t chunk = (32u << 20) / in_row;
@@ -278,6 +326,81 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
     return rc;
 }
 
+// ---- optional call log (the run-time counterpart of the reference's VIT_WRITE_LOGFILE build,
+// deconvolve.cpp:568-621 / rschecksf.cpp:103-185): one line per API call with the call index, wall-clock entry
+// time, time since the previous call, thread id, call duration, the number of calls in flight when this one
+// returned ("ReE", the reference's re-entrancy counter), the frame / superframe shape and the buffer addresses.
+// Enabled by VITERBI_B200_LOG=<file>, read by initialize() and on first use; off by default. ------------------
+struct CallLogFile {
+    std::mutex mu;
+    FILE* fp = nullptr;
+    std::string path;
+    unsigned long long counter = 0;
+    std::chrono::steady_clock::time_point last{};
+    bool have_last = false;
+};
+CallLogFile g_log;
+std::atomic<int> g_log_on{-1};  // -1 not configured yet, 0 off, 1 on
+std::atomic<int> g_calls_in_flight{0};
+
+void configure_call_log() {
+    const char* env = getenv("VITERBI_B200_LOG");
+    std::lock_guard<std::mutex> lock(g_log.mu);
+    const std::string want = (env && *env) ? env : "";
+    if (want != g_log.path || g_log_on.load() < 0) {
+        if (g_log.fp) fclose(g_log.fp);
+        g_log.fp = want.empty() ? nullptr : fopen(want.c_str(), "a");
+        g_log.path = want;
+        g_log.have_last = false;
+    }
+    g_log_on.store(g_log.fp ? 1 : 0);
+}
+
+class CallLog {
+  public:
+    CallLog(const char* fn, unsigned shape, size_t n, const void* in, const void* out)
+        : fn_(fn), shape_(shape), n_(n), in_(in), out_(out) {
+        if (g_log_on.load(std::memory_order_relaxed) < 0) configure_call_log();
+        on_ = g_log_on.load(std::memory_order_relaxed) == 1;
+        if (!on_) return;
+        g_calls_in_flight.fetch_add(1);
+        wall_ = std::chrono::system_clock::now();
+        t0_ = std::chrono::steady_clock::now();
+    }
+    void result(int rc) { rc_ = rc; }
+    ~CallLog() {
+        if (!on_) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        const int others = g_calls_in_flight.fetch_sub(1) - 1;
+        const double us = std::chrono::duration<double, std::micro>(t1 - t0_).count();
+        const auto since_epoch = std::chrono::duration_cast<std::chrono::microseconds>(wall_.time_since_epoch()).count();
+        const time_t secs = (time_t)(since_epoch / 1000000);
+        struct tm tmv;
+        localtime_r(&secs, &tmv);
+        const size_t tid = std::hash<std::thread::id>()(std::this_thread::get_id()) % 100000;
+        std::lock_guard<std::mutex> lock(g_log.mu);
+        if (!g_log.fp) return;
+        const double dt_ms = g_log.have_last ? std::chrono::duration<double, std::milli>(t0_ - g_log.last).count() : 0.0;
+        g_log.last = t0_;
+        g_log.have_last = true;
+        fprintf(g_log.fp, "%6llu  %02d:%02d:%02d.%06lld  dT: %8.3f ms  TID: %5zu  %s: %9.1f us  ReE: %d  shape: %4u  n: %zu  "
+                          "In: %p  Out: %p  rc: %d\n",
+                g_log.counter++, tmv.tm_hour, tmv.tm_min, tmv.tm_sec, (long long)(since_epoch % 1000000), dt_ms, tid, fn_, us,
+                others, shape_, n_, in_, out_, rc_);
+        fflush(g_log.fp);
+    }
+
+  private:
+    const char* fn_;
+    unsigned shape_;
+    size_t n_;
+    const void *in_, *out_;
+    bool on_ = false;
+    int rc_ = 0;
+    std::chrono::system_clock::time_point wall_;
+    std::chrono::steady_clock::time_point t0_;
+};
+
 }  // namespace
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -295,8 +418,13 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------
 int deconvolve(unsigned int framebits, unsigned int* piData, int inputLength, unsigned char* output) {
     (void)inputLength;
-    if (g_save_mode.load()) return 1;  // decon_savemode, viterbi_helpers.asm:183-186
-    const int rc = vit_host(framebits, piData, true, 1, output);
+    CallLog log("deco", framebits, 1, piData, output);
+    if (g_save_mode.load()) {  // decon_savemode, viterbi_helpers.asm:183-186
+        log.result(1);
+        return 1;
+    }
+    const int rc = vit_host(framebits, piData, SymFormat::U32, 1, output);
+    log.result(rc == FEC_OK ? 0 : 1);
     if (rc == FEC_OK) return 0;
     // The reference latches save mode after a fault inside the decoder (NULL buffers give an
     // access violation there, viterbi-benchmark.cpp:457-464); a device failure is our equivalent.
@@ -308,9 +436,11 @@ int deconvolve(unsigned int framebits, unsigned int* piData, int inputLength, un
 int RScheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsigned char* outVector) {
     (void)startIx;
     if (RSDims == 0) return 0;  // the reference's column loop does not execute
+    CallLog log("rssf", RSDims, 1, p, outVector);
     int32_t ret = -1;
     const int rc = rs_host(p, RSDims, 1, outVector, &ret);
-    if (rc != FEC_OK) return -1;  // exc_handler.cpp:208-211
+    if (rc != FEC_OK) ret = -1;  // exc_handler.cpp:208-211
+    log.result(ret);
     return ret;
 }
 
@@ -321,6 +451,7 @@ int RSCheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsign
 int initialize(void) {
     g_save_mode.store(0);  // dllmain.cpp:157
     t_error.clear();
+    configure_call_log();  // the reference re-reads its configuration here (dllmain.cpp:158 -> SetupDLL)
     const char* env = getenv("VITERBI_B200_DEVICE");
     if (env && *env) g_device.store(atoi(env));
     return device_state() != nullptr;
@@ -334,11 +465,17 @@ void WakeUpYMM(void) {}
 // batched API
 // ---------------------------------------------------------------------------------------------
 int viterbi_deconvolve_batch(unsigned int framebits, const uint8_t* syms, size_t n, uint8_t* out) {
-    return vit_host(framebits, syms, false, n, out);
+    CallLog log("deco_batch", framebits, n, syms, out);
+    const int rc = vit_host(framebits, syms, SymFormat::U8, n, out);
+    log.result(rc);
+    return rc;
 }
 
 int viterbi_deconvolve_batch_u32(unsigned int framebits, const uint32_t* syms, size_t n, uint8_t* out) {
-    return vit_host(framebits, syms, true, n, out);
+    CallLog log("deco_batch_u32", framebits, n, syms, out);
+    const int rc = vit_host(framebits, syms, SymFormat::U32, n, out);
+    log.result(rc);
+    return rc;
 }
 
 int viterbi_deconvolve_batch_device(unsigned int framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
@@ -371,8 +508,51 @@ int viterbi_deconvolve_batch_u32_device(unsigned int framebits, const uint32_t* 
     return rc;
 }
 
+int viterbi_deconvolve_batch_punctured(unsigned int framebits, const uint8_t* rx, size_t rx_per_frame, const uint8_t* keep,
+                                       unsigned int erasure, size_t n, uint8_t* out) {
+    CallLog log("deco_batch_punct", framebits, n, rx, out);
+    const int rc = vit_host(framebits, rx, SymFormat::Punctured, n, out, keep, rx_per_frame, erasure);
+    log.result(rc);
+    return rc;
+}
+
+int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint8_t* d_rx, size_t rx_per_frame,
+                                              const uint8_t* keep, unsigned int erasure, size_t n, uint8_t* d_out,
+                                              void* stream) {
+    if (!vit_args_ok(framebits)) return bad_arg("framebits must be even and <= 9216");
+    if (n == 0 || framebits == 0) return FEC_OK;
+    if (!d_rx || !d_out || !keep) return bad_arg("null pointer");
+    if (erasure > 255) return bad_arg("erasure must be 0..255");
+    std::vector<int32_t> idx;
+    if (!puncture_index(framebits, keep, rx_per_frame, idx)) return bad_arg("keep pattern does not match rx_per_frame");
+    DeviceState* st = device_state();
+    if (!st) return FEC_ERR_DEVICE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nsym = 4 * ((size_t)framebits + 6);
+    void *d_idx = nullptr, *d_syms = nullptr;
+    if (fail(cudaMallocAsync(&d_idx, nsym * sizeof(int32_t), s), "cudaMallocAsync(index table)")) return FEC_ERR_DEVICE;
+    if (fail(cudaMallocAsync(&d_syms, nsym * n, s), "cudaMallocAsync(expanded symbols)")) {
+        (void)cudaFreeAsync(d_idx, s);
+        return FEC_ERR_DEVICE;
+    }
+    // idx is pageable: cudaMemcpyAsync returns once it has been staged, so the vector may die with this call
+    int rc = (fail(cudaMemcpyAsync(d_idx, idx.data(), nsym * sizeof(int32_t), cudaMemcpyHostToDevice, s), "H2D index table") ||
+              fail(launch_depuncture(d_rx, rx_per_frame, (const int32_t*)d_idx, framebits, erasure, (uint8_t*)d_syms, n,
+                                     st->num_sms, s),
+                   "depuncture kernel"))
+                 ? FEC_ERR_DEVICE
+                 : FEC_OK;
+    if (rc == FEC_OK) rc = vit_device(st, framebits, (const uint8_t*)d_syms, n, d_out, s, nullptr, 0);
+    (void)cudaFreeAsync(d_syms, s);
+    (void)cudaFreeAsync(d_idx, s);
+    return rc;
+}
+
 int rs_check_superframe_batch(const uint8_t* in, unsigned int RSDims, size_t n, uint8_t* out, int32_t* ret) {
-    return rs_host(in, RSDims, n, out, ret);
+    CallLog log("rssf_batch", RSDims, n, in, out);
+    const int rc = rs_host(in, RSDims, n, out, ret);
+    log.result(rc);
+    return rc;
 }
 
 int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
@@ -416,7 +596,6 @@ int dabplus_decode_superframes(unsigned int framebits, const uint8_t* syms, size
     int dev;
     DeviceState* st = device_state(&dev);
     if (!st) return FEC_ERR_DEVICE;
-    std::lock_guard<std::mutex> lock(g_pipe.mu);
     if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
     const unsigned rsdims = framebits / 192u;
     const size_t nsym = 4 * ((size_t)framebits + 6), in_row = 5 * nsym, out_row = 110 * (size_t)rsdims;

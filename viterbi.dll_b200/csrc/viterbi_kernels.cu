@@ -478,6 +478,28 @@ __global__ void __launch_bounds__(256) compact_symbols_kernel(const uint4* __res
     }
 }
 
+// Depuncturing front end: the receiver transmits only the code bits its puncturing
+// vector keeps; the step before deconvolve() puts them back at their positions in the rate-1/4 mother-code
+// layout and fills the punctured positions with the erasure value (the soft-symbol midpoint).  idx[p] is the
+// position of mother-code symbol p inside a received row, or -1 when it was punctured.  One thread builds the
+// four symbols of one trellis step (one aligned 32-bit store).
+__global__ void __launch_bounds__(256) depuncture_kernel(const uint8_t* __restrict__ rx, size_t rx_per_frame,
+                                                         const int4* __restrict__ idx, uint32_t steps,
+                                                         uint32_t erasure, uint32_t* __restrict__ out, size_t n) {
+    const size_t total = n * (size_t)steps;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / steps;
+        const uint32_t q = (uint32_t)(i - f * steps);
+        const int4 ix = __ldg(idx + q);
+        const uint8_t* row = rx + f * rx_per_frame;
+        const uint32_t b0 = ix.x >= 0 ? __ldg(row + ix.x) : erasure;
+        const uint32_t b1 = ix.y >= 0 ? __ldg(row + ix.y) : erasure;
+        const uint32_t b2 = ix.z >= 0 ? __ldg(row + ix.z) : erasure;
+        const uint32_t b3 = ix.w >= 0 ? __ldg(row + ix.w) : erasure;
+        out[i] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+}
+
 size_t viterbi_scratch_bytes(int grid_blocks, uint32_t framebits) {
     return kVitScratchHeader + (size_t)grid_blocks * (size_t)(framebits + 6) * 32 * sizeof(uint4);
 }
@@ -518,6 +540,20 @@ cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned 
     const unsigned long long cap = (unsigned long long)num_sms * 32;
     const unsigned grid = (unsigned)(nframes < cap ? nframes : cap);
     viterbi_warp_kernel<<<grid, 32, smem, stream>>>(d_syms, d_out, nframes, framebits);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
+                              uint32_t erasure, uint8_t* d_syms, size_t nframes, int num_sms, cudaStream_t stream) {
+    if (nframes == 0) return cudaSuccess;
+    const uint32_t steps = framebits + 6;
+    const size_t total = nframes * (size_t)steps;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    depuncture_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rx, rx_per_frame, (const int4*)d_idx, steps, erasure & 0xFFu,
+                                                          (uint32_t*)d_syms, nframes);
     count_launch();
     return cudaGetLastError();
 }

@@ -88,6 +88,62 @@ def lcg_symbols(seed: int, count: int) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------
+# Puncturing (the transmitter side of the depuncturing front end; not in viterbi.dll, which receives the
+# already expanded rate-1/4 stream).  DAB punctures the mother code in blocks of 128 code bits = four
+# repetitions of a 32-bit vector V_PI that keeps 8 + PI bits, PI = 1..24; the 24 tail code bits use a fixed
+# vector that keeps 12.  The vectors below follow that structure (each PI adds one kept bit to PI - 1); the
+# decoder API takes the pattern as data, so nothing on the decode path depends on this table.
+# ---------------------------------------------------------------------------
+_PI_ORDER = (0, 1, 4, 8, 12, 16, 20, 24, 28,      # PI = 1 keeps these 9 positions
+             17, 9, 25, 5, 21, 13, 29,            # PI = 2..8: the second bit of each group of four
+             2, 18, 10, 26, 6, 22, 14, 30,        # PI = 9..16: the third bit
+             3, 19, 11, 27, 7, 23, 15, 31)        # PI = 17..24: the fourth bit
+
+
+def puncture_vector(pi: int) -> np.ndarray:
+    """32-entry keep vector with 8 + pi ones (pi = 1..24)."""
+    if not 1 <= pi <= 24:
+        raise ValueError("PI must be 1..24")
+    v = np.zeros(32, dtype=np.uint8)
+    v[list(_PI_ORDER[: 8 + pi])] = 1
+    return v
+
+
+TAIL_VECTOR = np.array([1, 1, 0, 0] * 6, dtype=np.uint8)  # 24 tail code bits -> 12
+
+
+def puncture_pattern(framebits: int, segments) -> np.ndarray:
+    """keep pattern [4*(F+6)] for a frame whose 4*F info-part code bits are cut into 128-bit blocks:
+    segments = [(number_of_blocks, PI), ...] must cover 4*F/128 blocks; the 24 tail bits use TAIL_VECTOR."""
+    if (4 * framebits) % 128:
+        raise ValueError("framebits must be a multiple of 32")
+    parts = [np.tile(puncture_vector(pi), 4 * nblk) for nblk, pi in segments]
+    keep = np.concatenate(parts + [TAIL_VECTOR])
+    if keep.size != 4 * (framebits + 6):
+        raise ValueError("segments do not cover the frame")
+    return keep
+
+
+def fic_puncture_pattern() -> np.ndarray:
+    """Transmission-mode-I FIC shape: 768 info bits, 21 blocks at PI = 16, 3 blocks at PI = 15, tail:
+    3096 mother-code bits -> 2304 transmitted."""
+    return puncture_pattern(768, [(21, 16), (3, 15)])
+
+
+def puncture(syms: np.ndarray, keep: np.ndarray) -> np.ndarray:
+    """[n, 4*(F+6)] -> the transmitted symbols only [n, keep.sum()]."""
+    return np.ascontiguousarray(syms[:, np.asarray(keep, dtype=bool)])
+
+
+def depuncture(rx: np.ndarray, keep: np.ndarray, erasure: int = 128) -> np.ndarray:
+    """Host restatement of the expansion (for the checker side of the parity tests)."""
+    keep = np.asarray(keep, dtype=bool)
+    out = np.full((rx.shape[0], keep.size), erasure, dtype=np.uint8)
+    out[:, keep] = rx
+    return out
+
+
+# ---------------------------------------------------------------------------
 # torch generators (device-side synthetic input for the large benchmark configs)
 # ---------------------------------------------------------------------------
 def make_frames_torch(n: int, framebits: int, ebn0_db: float, seed: int, device, chunk: int = 8192,
