@@ -439,6 +439,37 @@ def run_b200(args):
                                      "viterbi_gbit_per_s": nsf * 5 * world * mf / (ms_pipe * 1e-3) / 1e9, "ms_per_step": ms_pipe}
         del msym, mout, mbits, psym
         torch.cuda.empty_cache()
+        # depuncturing front end: the same FIC batch sent as the 2,304 transmitted symbols per frame
+        # (FIC-shaped puncturing) instead of the 3,096 expanded ones, host buffers, end to end.  The decoded
+        # bits differ from the unpunctured run (erasures carry no information); parity of this path is in tests/.
+        if f == 768 and not args.no_e2e:
+            import ctypes
+
+            keep = dabgen.fic_puncture_pattern()
+            kidx = torch.from_numpy(np.flatnonzero(keep)).to(dev)
+            h_rx = torch.empty((n, int(keep.sum())), dtype=torch.uint8, pin_memory=True)
+            h_rx.copy_(syms.index_select(1, kidx))
+            h_pout = torch.empty((n, nout), dtype=torch.uint8, pin_memory=True)
+            torch.cuda.synchronize()
+
+            def punct_step():
+                rc = vb.lib.viterbi_deconvolve_batch_punctured(f, h_rx.data_ptr(), h_rx.shape[1],
+                                                               keep.ctypes.data_as(ctypes.c_void_p), 128, n, h_pout.data_ptr())
+                if rc != 0:
+                    raise RuntimeError("viterbi_deconvolve_batch_punctured rc=%d" % rc)
+
+            for _ in range(3):
+                punct_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                punct_step()
+            dtp = max_over_ranks(time.perf_counter() - t0) / 10
+            extra["e2e_punctured_fic"] = {"workload": "same %d FIC frames per GPU as 2304 transmitted symbols each + keep pattern "
+                                                      "(21 blocks PI=16, 3 blocks PI=15, tail)" % n,
+                                          "value": n * world * f / dtp / 1e9, "unit": "Gbit/s", "ms_per_step": dtp * 1e3,
+                                          "h2d_bytes_per_step": n * int(keep.sum()), "d2h_bytes_per_step": n * nout,
+                                          "api": "viterbi_deconvolve_batch_punctured (pinned host buffers)"}
 
     # ---- gather of result bitstreams over NCCL (outside the timed region) -----------------------------
     gather_ms = None
