@@ -36,14 +36,19 @@ struct RsTables {
     uint8_t mulpow[NROOTS][256];  // mulpow[j-1][v] = v * alpha^j: one Chien step of the x^j term
 };
 
-__constant__ RsTables c_tables;
+// In global memory, not __constant__: a block stages them with tid-strided reads, which are coalesced loads
+// here but 32 serialised fetches per warp from the constant cache.
+__device__ RsTables c_tables;
 
 // Block-shared copies of the tables.  They are file-scope __shared__ objects (not pointers handed down
 // through function arguments) so that every lookup compiles to an LDS with an immediate offset.
 __shared__ uint4 s_lfsr[256];
 __shared__ uint8_t s_ato[768];
 __shared__ uint8_t s_iof[256];
-__shared__ uint8_t s_mulpow[NROOTS * 256];
+// Chien-search step tables.  Entry [j][v] is not the product v * alpha^(j+1) itself but the shared-memory
+// ADDRESS of the entry of that product in the same table, so one step of one term is a single dependent LDS
+// (no index arithmetic, no window-base add).  The array is 1 KB-aligned, so address = table base | 4 * value.
+__shared__ __align__(1024) uint32_t s_next[NROOTS * 256];
 
 // rschecksf.cpp:50-52
 __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u) >> 24; }
@@ -51,8 +56,8 @@ __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u)
 // Chien search (rschecksf.cpp:296-320): evaluate lambda at alpha^i for i = 1..255 and record the
 // roots, stopping once deg(lambda) roots are found.  The reference keeps the terms in index form and
 // adds j to the exponent of the x^j term every iteration; here the terms stay in polynomial form and
-// are multiplied by alpha^j through a 256-byte table -- the same field elements, one shared-memory
-// lookup per term and position instead of add + mod + lookup.
+// are multiplied by alpha^j through a table -- the same field elements, one shared-memory lookup per term and
+// position instead of add + mod + lookup (see s_next for what the table holds).
 // D is the largest degree in the warp (warp-uniform, so the warp runs ONE instantiation instead of
 // serialising one loop per distinct degree); coefficients above a lane's own degree are zero and
 // stay zero under the multiplication.  A degree-d polynomial has at most d roots, so running past a
@@ -60,24 +65,42 @@ __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u)
 template <int D>
 __device__ __forceinline__ int chien(const uint32_t (&lam_poly)[NROOTS + 1], uint32_t (&root)[NROOTS + 1], int deg,
                                      unsigned mask) {
-    uint32_t term[D];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_next);
+    uint32_t term[D];      // shared-memory address of the table entry of the current term value
+    uint32_t target = 4u;  // XOR of the D addresses when the terms sum to 1, i.e. lambda(alpha^i) == 0
 #pragma unroll
-    for (int j = 0; j < D; j++) term[j] = lam_poly[j + 1];
+    for (int j = 0; j < D; j++) {
+        term[j] = base + (uint32_t)j * 1024u + 4u * lam_poly[j + 1];
+        target ^= base + (uint32_t)j * 1024u;
+    }
+    // keep the loop-invariant in a register: left alone, the compiler re-derives it from the shared-window base
+    // (S2UR + 10 more instructions) in every iteration
+    asm volatile("" : "+r"(target));
     int count = 0;
-    for (int i = 1; i <= NN; i++) {
-        uint32_t q = 1;
+    for (int i0 = 1; i0 <= NN; i0 += 8) {  // 8 positions per trip; roots are rare, so they are only flagged here
+        uint32_t hits = 0;
 #pragma unroll
-        for (int j = 0; j < D; j++) {
-            term[j] = s_mulpow[j * 256 + term[j]];
-            q ^= term[j];
-        }
-        if (q == 0 && count < deg) {
+        for (int u = 0; u < 8; u++) {
+            uint32_t x = 0;
 #pragma unroll
-            for (int c = 0; c < NROOTS; c++)
-                if (c == count) root[c] = (uint32_t)i;
-            count++;
+            for (int j = 0; j < D; j++) {
+                asm volatile("ld.shared.u32 %0, [%0];" : "+r"(term[j]));
+                x ^= term[j];
+            }
+            if (x == target) hits += 1u << u;
         }
-        if ((i & 7) == 0 && !__any_sync(mask, count < deg)) break;  // every lane has all its roots
+        if (i0 + 7 > NN) hits &= 0x7Fu;  // position 256 does not exist
+        while (hits) {  // a degree-d lambda has at most d roots, so count never passes deg
+            const int u = __ffs((int)hits) - 1;
+            hits &= hits - 1;
+            if (count < deg) {
+#pragma unroll
+                for (int c = 0; c < NROOTS; c++)
+                    if (c == count) root[c] = (uint32_t)(i0 + u);
+                count++;
+            }
+        }
+        if (!__any_sync(mask, count < deg)) break;  // every lane has all its roots
     }
     return count;
 }
@@ -231,7 +254,7 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, unsigned mask) {
 
 }  // namespace
 
-// One block = `sf_per_block` whole superframes; static shared memory holds the tables (7.5 KB), dynamic:
+// One block = `sf_per_block` whole superframes; static shared memory holds the tables (15 KB), dynamic:
 //   [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
 __global__ void __launch_bounds__(kRsThreads)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
@@ -246,9 +269,14 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     for (uint32_t i = tid; i < 256; i += blockDim.x) s_lfsr[i] = c_tables.lfsr[i];
     for (uint32_t i = tid; i < 768; i += blockDim.x) s_ato[i] = c_tables.ato[i];
     for (uint32_t i = tid; i < 256; i += blockDim.x) s_iof[i] = c_tables.iof[i];
-    for (uint32_t i = tid; i < NROOTS * 256; i += blockDim.x) s_mulpow[i] = c_tables.mulpow[i >> 8][i & 255];
+    {
+        const uint32_t next_base = (uint32_t)__cvta_generic_to_shared(s_next);
+        for (uint32_t i = tid; i < NROOTS * 256; i += blockDim.x)
+            s_next[i] = next_base + (i & ~255u) * 4u + 4u * c_tables.mulpow[i >> 8][i & 255];
+    }
 
     const size_t sf_in = (size_t)CW * s, sf_out = (size_t)DATA * s;
+    const uint32_t inv_s = (uint32_t)((0x100000000ull + s - 1) / s);
     const unsigned long long nblk = (nsf + sf_per_block - 1) / sf_per_block;
     for (unsigned long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const unsigned long long sf0 = blk * sf_per_block;
@@ -306,8 +334,9 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                     reinterpret_cast<uint32_t*>(d + nhead)[w] = __byte_perm(tw[w], tw[w + 1], sel);
                 for (size_t i = nhead + nwords * 4 + tid; i < sf_out; i += blockDim.x) d[i] = t[i];
             } else if (fail > 0) {
-                for (size_t i = tid; i < sf_out; i += blockDim.x)
-                    if ((uint32_t)(i % s) < fail) d[i] = t[i];
+                // i % s through a multiply-high (s is launch-uniform; exact for i < 2^17, s <= 1024)
+                for (uint32_t i = tid; i < (uint32_t)sf_out; i += blockDim.x)
+                    if (i - __umulhi(i, inv_s) * s < fail) d[i] = t[i];
             }
         }
     }
@@ -375,7 +404,14 @@ cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* 
         configured = smem;
     }
     unsigned long long nblk = (nsf + spb - 1) / spb;
-    const unsigned long long cap = (unsigned long long)num_sms * 16;
+    // persistent grid: exactly the blocks that are resident at once, so each block stages the tables once
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rs_superframe_kernel, kRsThreads, smem) != cudaSuccess ||
+        per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 4;
+    }
+    const unsigned long long cap = (unsigned long long)num_sms * (unsigned)per_sm;
     if (nblk > cap) nblk = cap;
     rs_superframe_kernel<<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, nsf, s, spb);
     count_launch();
