@@ -439,6 +439,30 @@ def run_b200(args):
                                      "viterbi_gbit_per_s": nsf * 5 * world * mf / (ms_pipe * 1e-3) / 1e9, "ms_per_step": ms_pipe}
         del msym, mout, mbits, psym
         torch.cuda.empty_cache()
+        # the same batch through the QIRX word-per-symbol layout (what the drop-in deconvolve() takes): 4x the bytes
+        if not args.no_e2e:
+            h_s32 = torch.empty((n, nsym), dtype=torch.int32, pin_memory=True)
+            h_s32.copy_(syms.to(torch.int32))
+            h_o32 = torch.empty((n, nout), dtype=torch.uint8, pin_memory=True)
+            torch.cuda.synchronize()
+
+            def u32_step():
+                rc = vb.lib.viterbi_deconvolve_batch_u32(f, h_s32.data_ptr(), n, h_o32.data_ptr())
+                if rc != 0:
+                    raise RuntimeError("viterbi_deconvolve_batch_u32 rc=%d" % rc)
+
+            for _ in range(2):
+                u32_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                u32_step()
+            dtu = max_over_ranks(time.perf_counter() - t0) / 5
+            extra["e2e_u32_layout"] = {"workload": "same %d frames per GPU, one uint32 per soft symbol (QIRX layout), compacted on the device" % n,
+                                       "value": n * world * f / dtu / 1e9, "unit": "Gbit/s", "ms_per_step": dtu * 1e3,
+                                       "h2d_bytes_per_step": n * nsym * 4, "d2h_bytes_per_step": n * nout,
+                                       "api": "viterbi_deconvolve_batch_u32 (pinned host buffers)"}
+            del h_s32, h_o32
         # depuncturing front end: the same FIC batch sent as the 2,304 transmitted symbols per frame
         # (FIC-shaped puncturing) instead of the 3,096 expanded ones, host buffers, end to end.  The decoded
         # bits differ from the unpunctured run (erasures carry no information); parity of this path is in tests/.
