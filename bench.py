@@ -550,6 +550,7 @@ def run_b200(args):
         }
         print(json.dumps(line))
     if world > 1:
+        barrier()  # no rank tears its communicator down while another is still inside a collective
         dist.destroy_process_group()
     return 0
 

@@ -130,6 +130,10 @@ def main():
         assert all_ret.shape[0] == n_all and all_out.shape == (n_all, 110 * s)
         assert torch.equal(all_ret[rank * res_sf:(rank + 1) * res_sf], ret)
         del all_ret, all_out
+        # Every rank must have left the collective before any rank tears its communicator down: in the first
+        # 8-GPU run ranks that were done exited while three others were still inside the 5.9 GB all-gather,
+        # which then sat in the NCCL watchdog for its full 10 minutes.
+        barrier()
 
     # ---- CPU reference chain on a slice: bit-exact check + all-core timing (rank 0) ----------------------
     cpu = None
@@ -172,6 +176,7 @@ def main():
         if wrong:
             raise SystemExit("payload mismatch on accepted superframes")
     if world > 1:
+        barrier()
         dist.destroy_process_group()
 
 
