@@ -30,7 +30,8 @@ def build(name: str, flags: str) -> None:
             name = "rev_" + rev.replace("/", "_")
         objs = []
         for src, extra in ((vit_src, ["-Xptxas", "-O1"] + shlex.split(flags)),
-                           (os.path.join(CSRC, "rs_kernels.cu"), []), (os.path.join(CSRC, "fec_api.cu"), [])):
+                           (os.path.join(CSRC, "rs_kernels.cu"), shlex.split(flags)),
+                           (os.path.join(CSRC, "fec_api.cu"), shlex.split(flags))):
             obj = os.path.join(tmp, os.path.basename(src) + ".o")
             subprocess.run(BASE + extra + ["-c", "-o", obj, src], check=True)
             objs.append(obj)

@@ -5,6 +5,8 @@ the CPU checker as well, so a sanitizer-clean run is also a correct one.
 
     compute-sanitizer --tool memcheck  python profiles/sanitizer_smoke.py
     compute-sanitizer --tool racecheck python profiles/sanitizer_smoke.py
+
+(compute-sanitizer is closed on the round-1 GPU pool, so only the native run was done there: it passes.)
 """
 import os
 import sys
