@@ -22,6 +22,7 @@
 #include <cstdint>
 
 #include "fec_internal.h"
+#include "rs_chien_bitsliced.h"
 
 namespace fec {
 
@@ -62,9 +63,21 @@ __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u)
 // serialising one loop per distinct degree); coefficients above a lane's own degree are zero and
 // stay zero under the multiplication.  A degree-d polynomial has at most d roots, so running past a
 // lane's own early-exit point cannot change its count.
+// Largest warp degree that takes the bit-sliced search (rs_chien_bitsliced.h: 8 registers per term, no shared
+// memory).  Degrees above the correction capability t = 5 only occur for uncorrectable words and are rare; they
+// keep the table-driven search below so that the register budget of the kernel is set by the common case.
+#ifndef RS_CHIEN_BITSLICED_MAXD
+#define RS_CHIEN_BITSLICED_MAXD 5
+#endif
+constexpr int kChienBitslicedMaxD = RS_CHIEN_BITSLICED_MAXD;
+
 template <int D>
 __device__ __forceinline__ int chien(const uint32_t (&lam_poly)[NROOTS + 1], uint32_t (&root)[NROOTS + 1], int deg,
                                      unsigned mask) {
+    if constexpr (D <= kChienBitslicedMaxD) {
+        return rsbits::chien_bitsliced<D>(lam_poly, root, deg,
+                                          [mask](bool need) { return __any_sync(mask, need) != 0; });
+    }
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_next);
     uint32_t term[D];      // shared-memory address of the table entry of the current term value
     uint32_t target = 4u;  // XOR of the D addresses when the terms sum to 1, i.e. lambda(alpha^i) == 0
@@ -256,7 +269,13 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, unsigned mask) {
 
 // One block = `sf_per_block` whole superframes; static shared memory holds the tables (15 KB), dynamic:
 //   [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
-__global__ void __launch_bounds__(kRsThreads)
+// 7 blocks per SM is what shared memory allows (15 KB of tables + ~15.6 KB of tile per block); the launch bound
+// keeps the bit-sliced Chien search inside 72 registers (76 bytes of spills) instead of 96 registers and 5 blocks:
+// measured 445 vs 337 M superframes/s.
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 7
+#endif
+__global__ void __launch_bounds__(kRsThreads, RS_MIN_BLOCKS)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
                      unsigned long long nsf, uint32_t s, uint32_t sf_per_block) {
     extern __shared__ __align__(16) uint8_t smem[];
