@@ -17,6 +17,8 @@
 // (one 16-byte table row per data byte).  The remainder is zero iff all ten syndromes are zero,
 // so clean codewords stop there; otherwise S_i = rem(a^i) (100 table steps).  The syndromes are
 // the same field elements either way, so every later stage sees the reference's values.
+//
+// The Chien search uses no tables at all: it is bit-sliced over 32 positions (rs_chien_bitsliced.h).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -34,7 +36,6 @@ struct RsTables {
     uint8_t ato[768];   // alpha^(i mod 255), dllmain.cpp:145-146
     uint8_t iof[256];   // log, log(0) = 255, dllmain.cpp:131-143
     uint4 lfsr[256];    // c * (g(x) - x^10): coefficients x^0..x^9 in bytes 0..9
-    uint8_t mulpow[NROOTS][256];  // mulpow[j-1][v] = v * alpha^j: one Chien step of the x^j term
 };
 
 // In global memory, not __constant__: a block stages them with tid-strided reads, which are coalesced loads
@@ -46,76 +47,19 @@ __device__ RsTables c_tables;
 __shared__ uint4 s_lfsr[256];
 __shared__ uint8_t s_ato[768];
 __shared__ uint8_t s_iof[256];
-// Chien-search step tables.  Entry [j][v] is not the product v * alpha^(j+1) itself but the shared-memory
-// ADDRESS of the entry of that product in the same table, so one step of one term is a single dependent LDS
-// (no index arithmetic, no window-base add).  The array is 1 KB-aligned, so address = table base | 4 * value.
-__shared__ __align__(1024) uint32_t s_next[NROOTS * 256];
-
 // rschecksf.cpp:50-52
 __device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u) >> 24; }
 
-// Chien search (rschecksf.cpp:296-320): evaluate lambda at alpha^i for i = 1..255 and record the
-// roots, stopping once deg(lambda) roots are found.  The reference keeps the terms in index form and
-// adds j to the exponent of the x^j term every iteration; here the terms stay in polynomial form and
-// are multiplied by alpha^j through a table -- the same field elements, one shared-memory lookup per term and
-// position instead of add + mod + lookup (see s_next for what the table holds).
-// D is the largest degree in the warp (warp-uniform, so the warp runs ONE instantiation instead of
-// serialising one loop per distinct degree); coefficients above a lane's own degree are zero and
-// stay zero under the multiplication.  A degree-d polynomial has at most d roots, so running past a
-// lane's own early-exit point cannot change its count.
-// Largest warp degree that takes the bit-sliced search (rs_chien_bitsliced.h: 8 registers per term, no shared
-// memory).  Degrees above the correction capability t = 5 only occur for uncorrectable words and are rare; they
-// keep the table-driven search below so that the register budget of the kernel is set by the common case.
-#ifndef RS_CHIEN_BITSLICED_MAXD
-#define RS_CHIEN_BITSLICED_MAXD 5
-#endif
-constexpr int kChienBitslicedMaxD = RS_CHIEN_BITSLICED_MAXD;
-
+// Chien search (rschecksf.cpp:296-320): find the roots alpha^i, i = 1..255, of lambda, in ascending i, stopping
+// once deg(lambda) of them are found.  Bit-sliced, 32 positions at a time, no table lookups: see
+// rs_chien_bitsliced.h.  D is the largest degree in the warp (warp-uniform, so the warp runs ONE instantiation
+// instead of serialising one search per distinct degree); coefficients above a lane's own degree are zero and
+// contribute nothing.  A degree-d polynomial has at most d roots, so running past a lane's own early-exit point
+// cannot change its count.
 template <int D>
 __device__ __forceinline__ int chien(const uint32_t (&lam_poly)[NROOTS + 1], uint32_t (&root)[NROOTS + 1], int deg,
                                      unsigned mask) {
-    if constexpr (D <= kChienBitslicedMaxD) {
-        return rsbits::chien_bitsliced<D>(lam_poly, root, deg,
-                                          [mask](bool need) { return __any_sync(mask, need) != 0; });
-    }
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_next);
-    uint32_t term[D];      // shared-memory address of the table entry of the current term value
-    uint32_t target = 4u;  // XOR of the D addresses when the terms sum to 1, i.e. lambda(alpha^i) == 0
-#pragma unroll
-    for (int j = 0; j < D; j++) {
-        term[j] = base + (uint32_t)j * 1024u + 4u * lam_poly[j + 1];
-        target ^= base + (uint32_t)j * 1024u;
-    }
-    // keep the loop-invariant in a register: left alone, the compiler re-derives it from the shared-window base
-    // (S2UR + 10 more instructions) in every iteration
-    asm volatile("" : "+r"(target));
-    int count = 0;
-    for (int i0 = 1; i0 <= NN; i0 += 8) {  // 8 positions per trip; roots are rare, so they are only flagged here
-        uint32_t hits = 0;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            uint32_t x = 0;
-#pragma unroll
-            for (int j = 0; j < D; j++) {
-                asm volatile("ld.shared.u32 %0, [%0];" : "+r"(term[j]));
-                x ^= term[j];
-            }
-            if (x == target) hits += 1u << u;
-        }
-        if (i0 + 7 > NN) hits &= 0x7Fu;  // position 256 does not exist
-        while (hits) {  // a degree-d lambda has at most d roots, so count never passes deg
-            const int u = __ffs((int)hits) - 1;
-            hits &= hits - 1;
-            if (count < deg) {
-#pragma unroll
-                for (int c = 0; c < NROOTS; c++)
-                    if (c == count) root[c] = (uint32_t)(i0 + u);
-                count++;
-            }
-        }
-        if (!__any_sync(mask, count < deg)) break;  // every lane has all its roots
-    }
-    return count;
+    return rsbits::chien_bitsliced<D>(lam_poly, root, deg, [mask](bool need) { return __any_sync(mask, need) != 0; });
 }
 
 // Decode one codeword stored at col[k * stride], k = 0..119, in place.  Returns the number of
@@ -267,13 +211,14 @@ __device__ int rs_decode_column(uint8_t* col, uint32_t stride, unsigned mask) {
 
 }  // namespace
 
-// One block = `sf_per_block` whole superframes; static shared memory holds the tables (15 KB), dynamic:
+// One block = `sf_per_block` whole superframes; static shared memory holds the tables (5 KB), dynamic:
 //   [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
-// 7 blocks per SM is what shared memory allows (15 KB of tables + ~15.6 KB of tile per block); the launch bound
-// keeps the bit-sliced Chien search inside 72 registers (76 bytes of spills) instead of 96 registers and 5 blocks:
-// measured 445 vs 337 M superframes/s.
+// 8 blocks (32 warps) per SM: the launch bound holds the kernel to 64 registers.  Left alone the bit-sliced Chien
+// search takes 96 (degree <= 5) to 125 registers, i.e. 5 or 4 blocks; the spills the bound causes sit almost
+// entirely in the rare high-degree searches.  Measured on the bench mix: 337 M superframes/s unbounded, 455 M at 7
+// blocks, 464 M at 8, 457 M at 9, 400 M at 10.
 #ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 7
+#define RS_MIN_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(kRsThreads, RS_MIN_BLOCKS)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
@@ -288,11 +233,6 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
     for (uint32_t i = tid; i < 256; i += blockDim.x) s_lfsr[i] = c_tables.lfsr[i];
     for (uint32_t i = tid; i < 768; i += blockDim.x) s_ato[i] = c_tables.ato[i];
     for (uint32_t i = tid; i < 256; i += blockDim.x) s_iof[i] = c_tables.iof[i];
-    {
-        const uint32_t next_base = (uint32_t)__cvta_generic_to_shared(s_next);
-        for (uint32_t i = tid; i < NROOTS * 256; i += blockDim.x)
-            s_next[i] = next_base + (i & ~255u) * 4u + 4u * c_tables.mulpow[i >> 8][i & 255];
-    }
 
     const size_t sf_in = (size_t)CW * s, sf_out = (size_t)DATA * s;
     const uint32_t inv_s = (uint32_t)((0x100000000ull + s - 1) / s);
@@ -406,8 +346,6 @@ cudaError_t rs_upload_tables() {
             w[q] = row[4 * q] | (row[4 * q + 1] << 8) | (row[4 * q + 2] << 16) | ((uint32_t)row[4 * q + 3] << 24);
         h.lfsr[c] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    for (int j = 1; j <= NROOTS; j++)
-        for (unsigned v = 0; v < 256; v++) h.mulpow[j - 1][v] = mul((uint8_t)v, alpha[j]);
     return cudaMemcpyToSymbol(c_tables, &h, sizeof(h));
 }
 
