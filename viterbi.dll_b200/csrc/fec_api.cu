@@ -175,6 +175,16 @@ size_t host_chunk_frames() {
     return frames;
 }
 
+// Host-path chunk size of the RS calls in input bytes per pipeline stage (VITERBI_B200_RS_CHUNK_MB overrides).
+size_t rs_chunk_bytes() {
+    static const size_t bytes = [] {
+        const char* env = getenv("VITERBI_B200_RS_CHUNK_MB");
+        const long v = (env && *env) ? atol(env) : 16;  // 32 / 16 / 8 / 4 MB measured: 41.3 / 42.9 / 41.8 / 40.2 M superframes/s
+        return (size_t)(v >= 1 ? v : 16) << 20;
+    }();
+    return bytes;
+}
+
 bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= VITERBI_B200_MAX_FRAMEBITS; }
 
 // Enqueue one batch that is already in device memory.  Scratch is stream-ordered.
@@ -246,6 +256,20 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
         syms = s0.h_pin;
         bounce_out = (uint8_t*)s0.h_pin + in_pad;
         out = bounce_out;
+    }
+    // ... and when the warp-per-frame kernel would decode them anyway, it runs directly on the bounce buffer:
+    // pinned memory is mapped into the device's address space, the kernel stages the symbols into shared memory
+    // itself (compacting the u32 layout on the way) and writes the decoded bytes back through the mapping, so
+    // the call is one kernel launch and one synchronise -- no copy operations, no compaction kernel.
+    if (bounce_out && !punct && n < kVitWarpKernelMaxFrames && g_vit_kernel.load() != FEC_VITERBI_PAIR) {
+        Slot& s0 = g_pipe.slot[0];
+        const cudaError_t e =
+            is_u32 ? launch_viterbi_warp_u32((const uint32_t*)syms, bounce_out, n, framebits, st->num_sms, s0.stream)
+                   : launch_viterbi_warp((const uint8_t*)syms, bounce_out, n, framebits, st->num_sms, s0.stream);
+        if (fail(e, "viterbi warp kernel launch") || fail(cudaStreamSynchronize(s0.stream), "cudaStreamSynchronize"))
+            return FEC_ERR_DEVICE;
+        memcpy(user_out, bounce_out, out_bytes);
+        return FEC_OK;
     }
     // chunks are pipelined over kPipe streams: the H2D copy of chunk k+1, the kernel of chunk k and the
     // D2H copy of chunk k-1 overlap
@@ -327,7 +351,7 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
         out = bounce + in_pad;
         ret = reinterpret_cast<int32_t*>(bounce + in_pad + out_pad);
     }
-    size_t chunk = (32u << 20) / in_row;
+    size_t chunk = rs_chunk_bytes() / in_row;
     if (chunk < 1) chunk = 1;
     if (chunk > n) chunk = n;
     int rc = FEC_OK;

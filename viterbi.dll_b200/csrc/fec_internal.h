@@ -30,6 +30,8 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
                                 uint32_t framebits, int grid_blocks, cudaStream_t stream);
 cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
                                 int num_sms, cudaStream_t stream);
+cudaError_t launch_viterbi_warp_u32(const uint32_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
+                                    int num_sms, cudaStream_t stream);
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
                               uint32_t erasure, uint8_t* d_syms, size_t nframes, int num_sms, cudaStream_t stream);
 cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t nsymbols, int num_sms,

@@ -392,12 +392,18 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
 // it is used where the pair kernel cannot fill the machine: the single-frame drop-in call and batches
 // below kVitWarpKernelMaxFrames.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) viterbi_warp_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
+// kU32: the symbols arrive in QIRX's one-uint32-per-symbol layout (low byte used, deconvolve.cpp:219-228) and are
+// compacted while they are staged.  The decoded bytes are collected in shared memory and written out by the
+// whole warp, so both ends work on host-mapped (pinned) memory as well: the single-frame drop-in call runs this
+// kernel straight on the caller's bounce buffer, with no copy operations around it.
+template <bool kU32>
+__global__ void __launch_bounds__(32) viterbi_warp_kernel(const void* __restrict__ syms_any, uint8_t* __restrict__ out,
                                                           unsigned long long nframes, uint32_t framebits) {
     extern __shared__ __align__(16) uint8_t wsmem[];
     const uint32_t steps = framebits + 6, lane = threadIdx.x;
     uint32_t* s_sym = reinterpret_cast<uint32_t*>(wsmem);         // [steps] 4 symbols per step
     uint2* s_dec = reinterpret_cast<uint2*>(wsmem + 4 * (size_t)steps);  // [steps] {even, odd} ballots
+    uint8_t* s_out = wsmem + 12 * (size_t)steps;                  // [ceil(F/8)] decoded bytes
     const size_t outbytes = (framebits + 7) / 8;
 
     // branch masks of butterfly `lane` (const.asm:35-49 restated): 0xFF where the expected code bit is 1
@@ -408,9 +414,32 @@ __global__ void __launch_bounds__(32) viterbi_warp_kernel(const uint8_t* __restr
     const uint32_t srcA = lane >> 1, srcB = 16u + (lane >> 1);
 
     for (unsigned long long f = blockIdx.x; f < nframes; f += gridDim.x) {
-        const uint2* row = reinterpret_cast<const uint2*>(syms + f * 4 * (size_t)steps);
         __syncwarp();
-        for (uint32_t i = lane; i < steps / 2; i += 32) reinterpret_cast<uint2*>(s_sym)[i] = __ldg(row + i);
+        if (kU32) {
+            const uint4* row = reinterpret_cast<const uint4*>(syms_any) + f * (size_t)steps;  // one step per uint4
+            // eight loads in flight per lane: over PCIe (host-mapped input) each round trip costs ~1.5 us
+            for (uint32_t i0 = lane; i0 < steps; i0 += 32 * 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + 32 * u < steps) v[u] = __ldg(row + i0 + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + 32 * u < steps)
+                        s_sym[i0 + 32 * u] = (v[u].x & 0xFFu) | ((v[u].y & 0xFFu) << 8) | ((v[u].z & 0xFFu) << 16) | (v[u].w << 24);
+            }
+        } else {
+            const uint2* row = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(syms_any) + f * 4 * (size_t)steps);
+            for (uint32_t i0 = lane; i0 < steps / 2; i0 += 32 * 8) {
+                uint2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + 32 * u < steps / 2) v[u] = __ldg(row + i0 + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + 32 * u < steps / 2) reinterpret_cast<uint2*>(s_sym)[i0 + 32 * u] = v[u];
+            }
+        }
         __syncwarp();
 
         uint32_t A = (lane == 0) ? 0u : 63u, B = 63u;  // Locals256: M[0] = 0, others 63 (deconvolve.cpp:130-132)
@@ -449,7 +478,7 @@ __global__ void __launch_bounds__(32) viterbi_warp_kernel(const uint8_t* __restr
         // ChainBack (deconvolve.cpp:416-435) by lane 0, same 32-bit state register as the pair kernel:
         // state = h >> 26; its decision is bit (state >> 1) of the even / odd ballot word.
         if (lane == 0) {
-            uint8_t* o = out + f * outbytes;
+            uint8_t* o = s_out;
             uint32_t h = 0;
             int t = (int)framebits - 1;
             auto step = [&](const uint2 w, int tt) {
@@ -466,6 +495,8 @@ __global__ void __launch_bounds__(32) viterbi_warp_kernel(const uint8_t* __restr
                 for (int j = 0; j < 8; j++) step(w[j], t - j);
             }
         }
+        __syncwarp();
+        for (uint32_t i = lane; i < outbytes; i += 32) out[f * outbytes + i] = s_out[i];
     }
 }
 
@@ -525,23 +556,34 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
     return cudaGetLastError();
 }
 
-size_t viterbi_warp_smem_bytes(uint32_t framebits) { return 12 * (size_t)(framebits + 6); }
+size_t viterbi_warp_smem_bytes(uint32_t framebits) { return 12 * (size_t)(framebits + 6) + ((framebits + 7) / 8 + 15) / 16 * 16; }
 
-cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
-                                int num_sms, cudaStream_t stream) {
+template <bool kU32>
+static cudaError_t launch_viterbi_warp_t(const void* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
+                                         int num_sms, cudaStream_t stream) {
     if (nframes == 0) return cudaSuccess;
     const size_t smem = viterbi_warp_smem_bytes(framebits);
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(viterbi_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(viterbi_warp_kernel<kU32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     const unsigned long long cap = (unsigned long long)num_sms * 32;
     const unsigned grid = (unsigned)(nframes < cap ? nframes : cap);
-    viterbi_warp_kernel<<<grid, 32, smem, stream>>>(d_syms, d_out, nframes, framebits);
+    viterbi_warp_kernel<kU32><<<grid, 32, smem, stream>>>(d_syms, d_out, nframes, framebits);
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
+                                int num_sms, cudaStream_t stream) {
+    return launch_viterbi_warp_t<false>(d_syms, d_out, nframes, framebits, num_sms, stream);
+}
+
+cudaError_t launch_viterbi_warp_u32(const uint32_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
+                                    int num_sms, cudaStream_t stream) {
+    return launch_viterbi_warp_t<true>(d_syms, d_out, nframes, framebits, num_sms, stream);
 }
 
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
