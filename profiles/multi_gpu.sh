@@ -4,7 +4,7 @@ N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 $TR --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err
 tail -c 300 gpurun_out/bench_${N}gpu.err
-$TR --master-port 29512 profiles/e2e_scaling.py > gpurun_out/e2e_${N}gpu.json 2> gpurun_out/e2e_${N}gpu.err
+$TR --master-port 29512 tests/full_size/e2e_scaling.py > gpurun_out/e2e_${N}gpu.json 2> gpurun_out/e2e_${N}gpu.err
 tail -c 300 gpurun_out/e2e_${N}gpu.err
 python - <<PY
 import json

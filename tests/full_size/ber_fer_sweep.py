@@ -4,7 +4,7 @@ BER/FER of the B200 decoder next to the reference CPU decoder on the SAME soft s
 Every frame is decoded by both; outputs are compared bit for bit (so the two BER/FER columns are identical by
 construction -- the script asserts it and counts mismatching frames).  Prints one JSON line.
 
-    python profiles/ber_fer_sweep.py [--frames 262144] [--slice 32768]
+    python tests/full_size/ber_fer_sweep.py [--frames 262144] [--slice 32768]
 """
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)

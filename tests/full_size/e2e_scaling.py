@@ -1,9 +1,9 @@
 """BASELINE configs[4]: sharded end-to-end DAB+ decode -- 2^24 MSC frames (F=3072), Viterbi + superframe RS
 check on the device, 1/2/4/8 B200, next to the all-core host CPU reference.
 
-    python profiles/e2e_scaling.py                       (1 GPU)
+    python tests/full_size/e2e_scaling.py                       (1 GPU)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        profiles/e2e_scaling.py                          (N GPUs)
+        tests/full_size/e2e_scaling.py                          (N GPUs)
 
 Strong scaling: the job is --total-frames frames whatever N is.  Each rank owns total/N frames (whole
 superframes: 5 consecutive frames).  2^24 frames of soft symbols are 206 GB, more than one GPU holds, so a rank
@@ -28,7 +28,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)

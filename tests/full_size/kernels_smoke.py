@@ -3,8 +3,8 @@ native, so the sizes are tiny but cover: pair kernel with full and ragged groups
 u32 compaction, depuncturing, RS with s = 1..17 and failing columns, the DAB+ chain).  Outputs are compared with
 the CPU checker as well, so a sanitizer-clean run is also a correct one.
 
-    compute-sanitizer --tool memcheck  python profiles/sanitizer_smoke.py
-    compute-sanitizer --tool racecheck python profiles/sanitizer_smoke.py
+    compute-sanitizer --tool memcheck  python tests/full_size/kernels_smoke.py
+    compute-sanitizer --tool racecheck python tests/full_size/kernels_smoke.py
 
 (compute-sanitizer is closed on the round-1 GPU pool, so only the native run was done there: it passes.)
 """
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 

@@ -53,7 +53,7 @@ def test_punctured_fic_still_decodes_on_a_clean_channel(port):
 
 
 def test_torch_generators_agree_with_the_decoders(port):
-    """The device-side generators used by bench.py / profiles/e2e_scaling.py, run here on the CPU."""
+    """The device-side generators used by bench.py / tests/full_size/e2e_scaling.py, run here on the CPU."""
     sym, bits = dabgen.make_frames_torch(40, 96, 9.0, seed=1, device="cpu", want_bits=True)
     assert np.array_equal(port.deconvolve_batch(96, sym.numpy()), bits.numpy())
     rx, nerr = dabgen.make_superframes_torch(30, 3, seed=2, device="cpu", max_err=5)
