@@ -24,13 +24,16 @@
 #include <cstdint>
 
 #include "fec_internal.h"
-#include "rs_chien_bitsliced.h"
+#include "rs_decode.h"
 
 namespace fec {
 
 namespace {
 
-constexpr int NN = 255, NROOTS = 10, PAD = 135, CW = 120, DATA = 110;
+using rsdec::CW;
+using rsdec::DATA;
+using rsdec::NN;
+using rsdec::NROOTS;
 
 struct RsTables {
     uint8_t ato[768];   // alpha^(i mod 255), dllmain.cpp:145-146
@@ -47,167 +50,15 @@ __device__ RsTables c_tables;
 __shared__ uint4 s_lfsr[256];
 __shared__ uint8_t s_ato[768];
 __shared__ uint8_t s_iof[256];
-// rschecksf.cpp:50-52
-__device__ __forceinline__ uint32_t mod255(uint32_t x) { return (x * 0x1010102u) >> 24; }
-
-// Chien search (rschecksf.cpp:296-320): find the roots alpha^i, i = 1..255, of lambda, in ascending i, stopping
-// once deg(lambda) of them are found.  Bit-sliced, 32 positions at a time, no table lookups: see
-// rs_chien_bitsliced.h.  D is the largest degree in the warp (warp-uniform, so the warp runs ONE instantiation
-// instead of serialising one search per distinct degree); coefficients above a lane's own degree are zero and
-// contribute nothing.  A degree-d polynomial has at most d roots, so running past a lane's own early-exit point
-// cannot change its count.
-template <int D>
-__device__ __forceinline__ int chien(const uint32_t (&lam_poly)[NROOTS + 1], uint32_t (&root)[NROOTS + 1], int deg,
-                                     unsigned mask) {
-    return rsbits::chien_bitsliced<D>(lam_poly, root, deg, [mask](bool need) { return __any_sync(mask, need) != 0; });
-}
-
-// Decode one codeword stored at col[k * stride], k = 0..119, in place.  Returns the number of
-// roots found (= corrected symbols as the reference counts them), 0 for a clean word, -1 if
-// uncorrectable.  Called by all lanes of `mask` together: control flow is kept warp-uniform (clean
-// lanes ride along with all-zero syndromes, which Berlekamp-Massey turns into lambda = 1, degree 0,
-// zero roots, return value 0 -- exactly the reference's early return).
-__device__ int rs_decode_column(uint8_t* col, uint32_t stride, unsigned mask) {
-    const uint8_t* const ato = s_ato;
-    const uint8_t* const iof = s_iof;
-    const uint4* const lfsr = s_lfsr;
-    // ---- remainder of cw(x) mod g(x); cw[0] is the highest-degree coefficient -----------------
-    uint32_t r0 = 0, r1 = 0, r2 = 0;  // coefficients x^0..x^3 | x^4..x^7 | x^8,x^9
-#pragma unroll 4
-    for (int k = 0; k < CW; k++) {
-        const uint32_t c = r2 >> 8;  // coefficient of x^9 moves to x^10 and is reduced away
-        const uint4 row = lfsr[c];
-        r2 = ((r2 << 8) & 0xFF00u) | (r1 >> 24);
-        r1 = (r1 << 8) | (r0 >> 24);
-        r0 = (r0 << 8) | col[(size_t)k * stride];
-        r0 ^= row.x;
-        r1 ^= row.y;
-        r2 ^= row.z;
-    }
-    // all syndromes zero <=> remainder zero (rschecksf.cpp:224-230); skip the rest if the whole warp is clean
-    if (!__any_sync(mask, (r0 | r1 | r2) != 0u)) return 0;
-
-    // ---- syndromes S_i = rem(alpha^i), then index form (rschecksf.cpp:232-233) ------------------
-    uint32_t syn[NROOTS];  // 32-bit holders: byte arrays make the compiler pack/unpack registers
-    {
-        uint32_t lg[NROOTS];
-#pragma unroll
-        for (int k = 0; k < NROOTS; k++) {
-            const uint32_t v = ((k < 4 ? r0 : k < 8 ? r1 : r2) >> (8 * (k & 3))) & 0xFFu;
-            lg[k] = iof[v];
-        }
-#pragma unroll
-        for (int i = 0; i < NROOTS; i++) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int k = 0; k < NROOTS; k++)
-                if (lg[k] != NN) acc ^= ato[lg[k] + i * k];  // <= 254 + 81
-            syn[i] = iof[acc];
-        }
-    }
-
-    // ---- Berlekamp-Massey (rschecksf.cpp:236-284): lambda polynomial form, b / syn index form ---
-    uint32_t lam[NROOTS + 1], b[NROOTS + 1], nxt[NROOTS + 1];
-#pragma unroll
-    for (int i = 0; i <= NROOTS; i++) {
-        lam[i] = (i == 0) ? 1 : 0;
-        b[i] = (i == 0) ? 0 : NN;
-    }
-    int el = 0;
-#pragma unroll
-    for (int r = 1; r <= NROOTS; r++) {
-        uint32_t discr = 0;
-#pragma unroll
-        for (int i = 0; i < r; i++)
-            if (lam[i] != 0 && syn[r - i - 1] != NN) discr ^= ato[iof[lam[i]] + syn[r - i - 1]];
-        discr = iof[discr];
-        if (discr == NN) {
-#pragma unroll
-            for (int i = NROOTS; i > 0; i--) b[i] = b[i - 1];
-            b[0] = NN;
-        } else {
-            nxt[0] = lam[0];
-#pragma unroll
-            for (int i = 0; i < NROOTS; i++) {
-                nxt[i + 1] = lam[i + 1];
-                if (b[i] != NN) nxt[i + 1] ^= ato[discr + b[i]];
-            }
-            if (2 * el <= r - 1) {
-                el = r - el;
-#pragma unroll
-                for (int i = 0; i <= NROOTS; i++)
-                    b[i] = (lam[i] == 0) ? (uint32_t)NN : mod255(iof[lam[i]] - discr + NN);
-            } else {
-#pragma unroll
-                for (int i = NROOTS; i > 0; i--) b[i] = b[i - 1];
-                b[0] = NN;
-            }
-#pragma unroll
-            for (int i = 0; i <= NROOTS; i++) lam[i] = nxt[i];
-        }
-    }
-
-    uint32_t lam_poly[NROOTS + 1];
-    int deg_lambda = 0;
-#pragma unroll
-    for (int i = 0; i <= NROOTS; i++) {
-        lam_poly[i] = lam[i];
-        lam[i] = iof[lam[i]];
-        if (lam[i] != NN) deg_lambda = i;
-    }
-
-    // ---- Chien search, one instantiation per warp (largest degree present) ---------------------------
-    uint32_t root[NROOTS + 1];
-    int count = 0;
-    switch (__reduce_max_sync(mask, (unsigned)deg_lambda)) {
-        case 1: count = chien<1>(lam_poly, root, deg_lambda, mask); break;
-        case 2: count = chien<2>(lam_poly, root, deg_lambda, mask); break;
-        case 3: count = chien<3>(lam_poly, root, deg_lambda, mask); break;
-        case 4: count = chien<4>(lam_poly, root, deg_lambda, mask); break;
-        case 5: count = chien<5>(lam_poly, root, deg_lambda, mask); break;
-        case 6: count = chien<6>(lam_poly, root, deg_lambda, mask); break;
-        case 7: count = chien<7>(lam_poly, root, deg_lambda, mask); break;
-        case 8: count = chien<8>(lam_poly, root, deg_lambda, mask); break;
-        case 9: count = chien<9>(lam_poly, root, deg_lambda, mask); break;
-        case 10: count = chien<10>(lam_poly, root, deg_lambda, mask); break;
-        default: break;  // every lane has degree 0: nothing to search
-    }
-    if (deg_lambda != count) return -1;  // rschecksf.cpp:325-326
-
-    // ---- omega(x) = syn(x) lambda(x) mod x^10, index form (rschecksf.cpp:331-341) ----------------
-    const int deg_omega = deg_lambda - 1;
-    uint32_t om[NROOTS];
-#pragma unroll
-    for (int i = 0; i < NROOTS; i++) {
-        uint32_t tmp = 0;
-#pragma unroll
-        for (int j = 0; j <= i; j++)
-            if (syn[i - j] != NN && lam[j] != NN) tmp ^= ato[syn[i - j] + lam[j]];
-        om[i] = (i <= deg_omega) ? (uint32_t)iof[tmp] : (uint32_t)NN;
-    }
-
-    // ---- Forney (rschecksf.cpp:346-374) ---------------------------------------------------------
-#pragma unroll
-    for (int c = NROOTS - 1; c >= 0; c--) {
-        if (c >= count) continue;
-        const uint32_t rj = root[c];
-        if (rj < PAD + 1) continue;  // root in the virtual padding: counted, not applied
-        uint32_t num1 = 0;
-#pragma unroll
-        for (int i = NROOTS - 1; i >= 0; i--)
-            if (i <= deg_omega && om[i] != NN) num1 ^= ato[mod255(om[i] + (uint32_t)i * rj)];
-        if (!num1) continue;
-        const uint32_t num2 = ato[NN - rj];
-        uint32_t den = 0;
-        const int top = (deg_lambda < NROOTS - 1 ? deg_lambda : NROOTS - 1) & ~1;
-#pragma unroll
-        for (int i = 8; i >= 0; i -= 2)
-            if (i <= top && lam[i + 1] != NN) den ^= ato[mod255(lam[i + 1] + (uint32_t)i * rj)];
-        // exponent used unreduced: the table has 768 entries (viterbi.h:101, rschecksf.cpp:366-370)
-        col[(size_t)(rj - 1 - PAD) * stride] ^= ato[iof[num1] + iof[num2] + (NN - iof[den])];
-    }
-    return count;
-}
+// The per-codeword decoder lives in rs_decode.h (shared with the host check of the CPU suite); this is its device
+// policy: tables in shared memory, warp votes.
+struct DevicePolicy {
+    static __device__ __forceinline__ uint32_t ato(uint32_t i) { return s_ato[i]; }
+    static __device__ __forceinline__ uint32_t iof(uint32_t v) { return s_iof[v]; }
+    static __device__ __forceinline__ uint4 lfsr(uint32_t c) { return s_lfsr[c]; }
+    static __device__ __forceinline__ bool any(unsigned mask, bool p) { return __any_sync(mask, p) != 0; }
+    static __device__ __forceinline__ unsigned max(unsigned mask, unsigned v) { return __reduce_max_sync(mask, v); }
+};
 
 }  // namespace
 
@@ -263,7 +114,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
             const unsigned mask = __ballot_sync(0xffffffffu, c < ncw);
             if (c < ncw) {
                 const uint32_t n = c / s, j = c - n * s;
-                const int r = rs_decode_column(tile + n * sf_in + j, s, mask);
+                const int r = rsdec::rs_decode_column<DevicePolicy>(tile + n * sf_in + j, s, mask);
                 if (r < 0)
                     atomicMin(&s_fail[n], (int)j);
                 else if (r > 0)
