@@ -209,8 +209,10 @@ def run_reference(args):
         "impl": "reference", "metric": "viterbi_decoded_gbit_per_s", "value": value, "unit": "Gbit/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "batched FIC decode: %d frames x F=%d, AWGN Eb/N0=%.1f dB" % (n, f, args.ebn0),
-                   "implementation": what},
+        "config": {"workload": "batched FIC decode (BASELINE configs[1]): %d frames per GPU x F=%d info bits "
+                               "(+6 tail), 8-bit soft symbols, AWGN Eb/N0=%.1f dB" % (n, f, args.ebn0),
+                   "frames_per_gpu": n, "framebits": f, "implementation": what,
+                   "sample": "one %d-frame batch per step on the host cores, whatever --gpus says" % n},
         "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rs": {"metric": "rs_superframes_per_s", "value": rs_val, "unit": "superframes/s",
