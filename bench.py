@@ -11,18 +11,24 @@ A "step" is one pass of the hot path over one batch of synthetic input per GPU:
     viterbi-benchmark.cpp:293-311,658-670).  `value` = decoded info Gbit/s with inputs resident in HBM.
   * RS: BASELINE.json configs[3] -- 10^6 DAB+ superframes, s = 1..8 (125,000 each), 0-7 byte errors per
     codeword; reported under "rs" in the same JSON line (superframes/s).
-Weak scaling: every rank decodes its own batch of that size; no collective on the data path
-(frames are independent); the result bitstreams are gathered once with NCCL after the timed
-region (reported as gather_ms).
+Weak scaling: every rank decodes its own batch of that size; no collective on the data path (frames are
+independent).  Every rank checks a slice of its own results against the CPU checker (oracle/_ref) outside the
+timed regions; the mismatch counts are all-reduced into `parity_mismatches`.
 
-The JSON line also carries: e2e (same metric through the C-ABI host-pointer call, pinned host
-buffers, H2D + D2H inside the timed region), roofline (HBM view, contract shape) and
-roofline_int_alu (the bound that actually applies to the ACS kernel), cpu_baseline (the
-reference's own decoder from oracle/_ref on this box's host cores), clocks, gpu_launches.
+Other keys of the JSON line:
+  e2e            same metric through the C-ABI host-pointer call, pinned host buffers, H2D + D2H inside the timed region
+  roofline       the bound that applies to the ACS kernel: warp-instruction issue slots (592 sub-partitions x SM clock),
+                 from the per-launch instruction count of a committed ncu capture; HBM and SURVEY-8(d) views inside it
+  cpu_baseline   the reference's own decoder from oracle/_ref on this box's host cores (rank 0, N = 1)
+  extra.msc      BASELINE configs[2] shape (262,144 MSC frames per GPU)
+  extra.dropin   BASELINE configs[0]: single-frame deconvolve() latency next to the CPU reference per call
+  extra.configs4 BASELINE configs[4]: 2^24 MSC frames -> superframes, Viterbi + RS on device, STRONG scaling over the
+                 N ranks, with the NCCL all-gather of the results inside the timed region, overlapped with compute
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -33,11 +39,42 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))  # oracle_lib (CPU baseline legs only)
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # oracle_lib (CPU checker legs only)
 
 FIC_FRAMES, FIC_BITS = 65536, 768
 RS_TOTAL = 1_000_000
 W_VIT_OPS_PER_STEP = 320.0  # u8 integer ops per trellis step
+SUBPARTITIONS = 148 * 4     # warp schedulers of a B200: one warp-instruction per clock each
+
+
+def load_dabgen():
+    """The traffic generator, loaded by path: importing the package would dlopen the product library, which the
+    reference arm must not map."""
+    spec = importlib.util.spec_from_file_location("fec_dabgen", os.path.join(ROOT, "viterbi.dll_b200", "dabgen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_config(args, world):
+    """`config` of the JSON line -- identical for both arms."""
+    n, f = args.frames, args.framebits
+    return {"workload": "batched FIC decode (BASELINE configs[1]): %d frames per GPU x F=%d info bits (+6 tail), "
+                        "8-bit soft symbols, AWGN Eb/N0=%.1f dB" % (n, f, args.ebn0),
+            "frames_per_gpu": n, "framebits": f, "ebn0_db": args.ebn0,
+            "parallelism": "independent frames, contiguous shards, no data-path collective",
+            "l2_policy": "input %d MB + decision scratch > 126 MB L2; no explicit flush" % (n * 4 * (f + 6) // 1000000)}
+
+
+def load_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        try:
+            with open(p) as fh:
+                return json.load(fh)
+        except ValueError:
+            return None
+    return None
 
 
 def load_peaks():
@@ -47,21 +84,6 @@ def load_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def load_int_peak():
-    """Measured ALU-pipe lane-op rate (profiles/intbench_r01.jsonl), T lane-ops/s."""
-    p = os.path.join(ROOT, "profiles", "intbench_r01.jsonl")
-    best = None
-    if os.path.exists(p):
-        for line in open(p):
-            try:
-                d = json.loads(line)
-            except ValueError:
-                continue
-            if d.get("op") in ("lop3", "viaddmnmx_u16x2", "iadd"):
-                best = max(best or 0.0, float(d["tera_laneops_per_s"]))
-    return (best, "measured (profiles/intbench_r01.jsonl)") if best else (18.6, "nominal 148 SM x 64 lanes x 1.965 GHz")
 
 
 class ClockSampler:
@@ -175,14 +197,29 @@ def time_cpu_rs(chk, rs_sets, threads: int, min_seconds: float):
     return done / dt, done
 
 
+def time_cpu_single_calls(chk, kind, framebits, sym_u32: np.ndarray, calls: int):
+    """viterbi-benchmark.cpp:332-348: `calls` single deconvolve() calls on one thread; returns us per call.
+    Raw ctypes calls on prepared pointers, the same way the GPU drop-in is timed."""
+    fn = chk.lib.ref_deconvolve if kind == "reference" else chk.lib.oracle_deconvolve
+    out = np.zeros((framebits + 7) // 8, dtype=np.uint8)
+    ptrs = [sym_u32[i].ctypes.data for i in range(sym_u32.shape[0])]
+    optr, m = out.ctypes.data, len(ptrs)
+    for i in range(min(calls, 50)):
+        fn(framebits, ptrs[i % m], 0, optr)
+    t0 = time.perf_counter()
+    for i in range(calls):
+        fn(framebits, ptrs[i % m], 0, optr)
+    return (time.perf_counter() - t0) / calls * 1e6
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU decoder on the host cores, same workload / metric."""
     rank, _, world = dist_env()
     if rank != 0:
         return 0
     import oracle_lib
-    from viterbi_dll_b200 import dabgen
 
+    dabgen = load_dabgen()
     chk, kind, what = cpu_checker()
     cores = oracle_lib.ncores()
     n, f = args.frames, args.framebits
@@ -204,16 +241,14 @@ def run_reference(args):
         per_s = 4000
         rs_sets = [(s, dabgen.make_superframes(per_s, s, seed=900 + s)[0]) for s in range(1, 9)]
         rs_val, _ = time_cpu_rs(chk, rs_sets, cores, 1.0)
-    sample = "%d FIC frames (F=%d) per step, all %d host threads, u32 symbol layout" % (n, f, cores)
+    sample = "%d FIC frames (F=%d) per step, all %d host threads, u32 symbol layout, one %d-frame batch per step " \
+             "whatever --gpus says" % (n, f, cores, n)
     line = {
         "impl": "reference", "metric": "viterbi_decoded_gbit_per_s", "value": value, "unit": "Gbit/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "batched FIC decode (BASELINE configs[1]): %d frames per GPU x F=%d info bits "
-                               "(+6 tail), 8-bit soft symbols, AWGN Eb/N0=%.1f dB" % (n, f, args.ebn0),
-                   "frames_per_gpu": n, "framebits": f, "implementation": what,
-                   "sample": "one %d-frame batch per step on the host cores, whatever --gpus says" % n},
-        "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind, "sample": sample, "implementation": what},
         "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rs": {"metric": "rs_superframes_per_s", "value": rs_val, "unit": "superframes/s",
                "sample": "8 x 4000 superframes, s=1..8, 0-7 errors/codeword, all host threads"} if rs_val else None,
@@ -239,6 +274,7 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    import oracle_lib
     import viterbi_dll_b200 as vb
     from viterbi_dll_b200 import dabgen
 
@@ -247,12 +283,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x: float, op="max") -> float:
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
         return float(t.item())
+
+    chk, chk_kind, chk_what = cpu_checker()
+    cores = oracle_lib.ncores()
+    chk_threads = max(1, cores // world)  # every rank checks its own slice at the same time
+    parity = {"frames_checked": 0, "superframes_checked": 0, "mismatches": 0}
 
     n, f = args.frames, args.framebits
     steps_per_frame, nsym, nout = f + 6, 4 * (f + 6), (f + 7) // 8
@@ -264,7 +305,8 @@ def run_b200(args):
         vb.deconvolve_batch_device(f, syms, out, stream)
 
     # ---- device-resident throughput ("value") -----------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         vit_step()
     barrier()
     launches0 = vb.kernel_launches()
@@ -279,35 +321,59 @@ def run_b200(args):
         torch.cuda.nvtx.range_pop()
     launches = vb.kernel_launches() - launches0
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = reduce_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     value = n * world * f / (ms_step * 1e-3) / 1e9
+    clocks = clk.summary()
+
+    cpu_syms = syms[: min(n, 32768)].cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
     # sanity inside the bench: decoded bits equal the payload on (nearly) all frames at 3 dB
     fer = float((out != bits).any(dim=1).float().mean().item()) if bits is not None else None
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------
+    # ---- parity of this rank's results against the CPU checker (outside the timed region, every rank) ----------
+    nchk = min(n, args.parity_frames)
+    sel = torch.linspace(0, n - 1, nchk, device=dev).long()  # spread over the whole batch, not just its head
+    want = chk.deconvolve_batch(f, syms.index_select(0, sel).cpu().numpy(), chk_threads)
+    parity["frames_checked"] += nchk
+    parity["mismatches"] += int((want != out.index_select(0, sel).cpu().numpy()).any(axis=1).sum())
+
+    # ---- roofline of the dominant kernel: instruction issue ------------------------------------------------------
     hbm_peak, hbm_src = load_peaks()
-    int_peak, int_src = load_int_peak()
-    alg_bytes = n * (nsym + nout)  # SURVEY 8(d): 4(F+6) + F/8 bytes per frame
+    int_peaks = load_json("int_peaks.json") or {}
+    int_peak = float(int_peaks.get("alu_pipe_tera_laneops_per_s", 18.56))
+    counts = (load_json("inst_counts.json") or {}).get("viterbi_pair_kernel", {})
     kern_s = (e0.elapsed_time(e1) / args.steps) * 1e-3  # this rank's average launch duration
+    groups = (n + 63) // 64
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+    issue_peak = SUBPARTITIONS * sm_mhz * 1e6  # warp-instructions per second the device can issue
+    inst_per_gs = counts.get("warp_inst_per_group_step")  # warp-instructions per 64-frame trellis step incl. traceback
+    alu_per_gs = counts.get("alu_pipe_inst_per_group_step")
+    alg_bytes = n * (nsym + nout)  # SURVEY 8(d): 4(F+6) + F/8 bytes per frame
     ach_gbs = alg_bytes / kern_s / 1e9
     ach_tops = W_VIT_OPS_PER_STEP * n * steps_per_frame / kern_s / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("viterbi_pair_kernel_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                "traffic": traffic, "peak_source": hbm_src, "kernel": "viterbi_pair_kernel",
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "HBM is not the limiter of the ACS recurrence; see roofline_int_alu"}
-    roofline_int = {"bound": "int_alu", "achieved": ach_tops, "peak": int_peak, "unit": "T u8-op/s vs T int32 lane-op/s",
-                    "frac": ach_tops / int_peak, "peak_source": int_src,
-                    "work": "320 u8 integer ops per trellis step x (F+6) steps x frames (SURVEY.md 8d); "
-                            "the kernel packs two 16-bit metrics per 32-bit lane-op, so frac can exceed 1"}
+    traffic = counts.get("dram_bytes_per_fic_launch") if (n, f) == (FIC_FRAMES, FIC_BITS) else None
+    if inst_per_gs:
+        inst = inst_per_gs * groups * steps_per_frame
+        ach_issue = inst / kern_s
+        roofline = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
+                    "frac": ach_issue / issue_peak, "traffic": traffic, "kernel": "viterbi_pair_kernel",
+                    "warp_inst_per_launch": inst,
+                    "alu_pipe_frac": (alu_per_gs * groups * steps_per_frame * 2 / kern_s / issue_peak) if alu_per_gs else None,
+                    "peak_source": "592 SM sub-partitions x %d MHz (median SM clock of this run's timed region)" % sm_mhz,
+                    "count_source": "profiles/inst_counts.json (%s)" % counts.get("source", "?"),
+                    "note": "the ACS recurrence is bound by warp-instruction issue (ALU pipe: 2 issue cycles per "
+                            "instruction); HBM and the SURVEY 8(d) op-count views follow"}
+    else:
+        roofline = {"bound": "issue", "achieved": None, "peak": issue_peak / 1e9, "unit": "G warp-inst/s", "frac": None,
+                    "traffic": traffic, "note": "profiles/inst_counts.json missing"}
+    roofline["hbm"] = {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                       "algorithmic_bytes_per_launch": alg_bytes, "peak_source": hbm_src}
+    roofline["int_alu_survey_8d"] = {"achieved": ach_tops, "peak": int_peak, "unit": "T u8-op/s vs T int32 lane-op/s",
+                                     "frac": ach_tops / int_peak,
+                                     "peak_source": int_peaks.get("source", "nominal 148 SM x 64 lanes x 1.965 GHz"),
+                                     "note": "320 u8 ops per trellis step (SURVEY 8d); two 16-bit metrics ride in each "
+                                             "32-bit lane-op, so this scale does not bound the kernel"}
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     e2e = None
@@ -330,13 +396,17 @@ def run_b200(args):
         for _ in range(k_e2e):
             e2e_step()
         torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        dt = reduce_ranks(time.perf_counter() - t0)
         barrier()
         if not torch.equal(h_out.to(dev), out):
-            raise RuntimeError("host-pointer path and device-pointer path disagree")
+            parity["mismatches"] += 1
         e2e = {"value": n * world * f * k_e2e / dt / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": n * nsym,
                "d2h_bytes_per_step": n * nout, "steps": k_e2e, "ms_per_step": dt / k_e2e * 1e3,
                "api": "viterbi_deconvolve_batch (pinned host buffers)"}
+        pcie = load_json("pcie_r02.json")
+        if pcie:
+            e2e["host_h2d_gbs_measured"] = pcie.get("h2d_gbs_by_ranks", {}).get(str(world))
+            e2e["pcie_source"] = "profiles/pcie_r02.json (aggregate pinned H2D over %d ranks)" % world
 
     # ---- RS superframe check -----------------------------------------------------------------------
     rs = None
@@ -366,16 +436,33 @@ def run_b200(args):
         torch.cuda.nvtx.range_pop()
         rs_launches = vb.kernel_launches() - l0
         barrier()
-        rs_ms = max_over_ranks(r0.elapsed_time(r1)) / args.steps
+        rs_ms = reduce_ranks(r0.elapsed_time(r1)) / args.steps
         rs_bytes = sum(per_s * (230 * s + 4) for s in range(1, 9))
-        rs_gbs = rs_bytes / (r0.elapsed_time(r1) / args.steps * 1e-3) / 1e9
+        rs_s_local = r0.elapsed_time(r1) / args.steps * 1e-3
+        rs_gbs = rs_bytes / rs_s_local / 1e9
+        rs_counts = (load_json("inst_counts.json") or {}).get("rs_superframe_kernel", {})
+        ncw = sum(per_s * s for s in range(1, 9))
+        rs_roof = {"bound": "issue", "unit": "G warp-inst/s", "peak": issue_peak / 1e9, "achieved": None, "frac": None,
+                   "traffic": rs_counts.get("dram_bytes_per_codeword", 0) * ncw or None,
+                   "hbm": {"achieved": rs_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rs_gbs / hbm_peak,
+                           "algorithmic_bytes_per_launch_set": rs_bytes}}
+        if rs_counts.get("warp_inst_per_codeword"):
+            ach = rs_counts["warp_inst_per_codeword"] * ncw / rs_s_local
+            rs_roof.update({"achieved": ach / 1e9, "frac": ach / issue_peak,
+                            "count_source": "profiles/inst_counts.json (%s)" % rs_counts.get("source", "?"),
+                            "note": "latency-bound table walks (LDS chains); issue slots are the nearest hard ceiling"})
+        # parity: a slice of every s against the checker
+        nsl = min(per_s, args.parity_superframes // 8)
+        for s, rx, o, r in sets:
+            w_out, w_ret = chk.rs_batch(rx[:nsl].cpu().numpy(), s, fill=0xEE, nthreads=chk_threads)
+            parity["superframes_checked"] += nsl
+            parity["mismatches"] += int((w_ret != r[:nsl].cpu().numpy()).sum()) + int((w_out != o[:nsl].cpu().numpy()).any(axis=1).sum())
         rs = {"metric": "rs_superframes_per_s", "value": per_s * 8 * world / (rs_ms * 1e-3), "unit": "superframes/s",
               "ms_per_step": rs_ms, "gpu_launches": rs_launches,
               "config": {"workload": "%d DAB+ superframes per GPU, s=1..8 (%d each), 0-7 byte errors per codeword"
                                      % (per_s * 8, per_s)},
               "uncorrectable_frac": float(sum((r < 0).float().mean().item() for _, _, _, r in sets) / 8),
-              "roofline": {"bound": "hbm", "achieved": rs_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rs_gbs / hbm_peak,
-                           "traffic": None, "algorithmic_bytes_per_launch_set": rs_bytes}}
+              "roofline": rs_roof}
         if not args.no_e2e:
             host = []
             for s, rx, o, _ in sets:
@@ -397,13 +484,18 @@ def run_b200(args):
             k_rs = 3
             for _ in range(k_rs):
                 rs_e2e_step()
-            dt = max_over_ranks(time.perf_counter() - t0)
+            dt = reduce_ranks(time.perf_counter() - t0)
+            for (s, _, h_o, h_r), (_, _, o, r) in zip(host, sets):
+                if not (torch.equal(h_o.to(dev), o) and torch.equal(h_r.to(dev), r)):
+                    parity["mismatches"] += 1
             rs["e2e"] = {"value": per_s * 8 * world * k_rs / dt, "unit": "superframes/s",
-                         "h2d_bytes_per_step": sum(per_s * 230 * s for s in range(1, 9)),
+                         "h2d_bytes_per_step": sum(per_s * 120 * s for s in range(1, 9)),
                          "d2h_bytes_per_step": sum(per_s * (110 * s + 4) for s in range(1, 9)),
-                         "api": "rs_check_superframe_batch (pinned host buffers; outVector travels both ways)"}
+                         "api": "rs_check_superframe_batch (pinned host buffers; the caller's outVector bytes of failing "
+                                "superframes are read by the kernel through the pinned mapping, nothing is uploaded)"}
+            del host
 
-    # ---- extras: MSC batch (BASELINE configs[2] shape) and the on-device DAB+ pipeline (configs[4] shape) ----
+    # ---- extras ---------------------------------------------------------------------------------------------------
     extra = {}
     if not args.no_extra:
         def timed(fn, reps):
@@ -417,31 +509,53 @@ def run_b200(args):
             b.record(stream)
             torch.cuda.synchronize()
             barrier()
-            return max_over_ranks(a.elapsed_time(b)) / reps
+            return reduce_ranks(a.elapsed_time(b)) / reps, a.elapsed_time(b) / reps
 
+        # MSC batch (BASELINE configs[2] shape, the largest single-GPU Viterbi config)
         mn, mf = args.msc_frames, 3072
         msym, mbits = dabgen.make_frames_torch(mn, mf, 3.0, seed=4321 + rank, device=dev, want_bits=True)
         mout = torch.zeros((mn, mf // 8), dtype=torch.uint8, device=dev)
-        ms_msc = timed(lambda: vb.deconvolve_batch_device(mf, msym, mout, stream), 5)
-        diff = (mout ^ mbits)
-        nbad = int((diff != 0).any(dim=1).sum().item())
+        ms_msc, ms_msc_local = timed(lambda: vb.deconvolve_batch_device(mf, msym, mout, stream), 5)
+        nbad = int(((mout ^ mbits) != 0).any(dim=1).sum().item())
+        msel = torch.linspace(0, mn - 1, min(mn, args.parity_frames // 4), device=dev).long()
+        mwant = chk.deconvolve_batch(mf, msym.index_select(0, msel).cpu().numpy(), chk_threads)
+        parity["frames_checked"] += int(msel.numel())
+        parity["mismatches"] += int((mwant != mout.index_select(0, msel).cpu().numpy()).any(axis=1).sum())
         extra["msc"] = {"workload": "batched MSC decode (BASELINE configs[2] shape): %d frames per GPU x F=3072, Eb/N0=3 dB" % mn,
                         "value": mn * world * mf / (ms_msc * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": ms_msc,
-                        "roofline_int_alu_frac": W_VIT_OPS_PER_STEP * mn * (mf + 6) / (ms_msc * 1e-3) / 1e12 / int_peak,
+                        "roofline_issue_frac": (inst_per_gs * ((mn + 63) // 64) * (mf + 6) / (ms_msc_local * 1e-3) / issue_peak)
+                        if inst_per_gs else None,
                         "frame_error_rate": nbad / mn}
-        # DAB+ pipeline on the first 5*k frames of the same symbols (payload is random, so most superframes
-        # fail RS: the point is the cost of the fused chain, parity is covered by tests/test_gpu_rs.py)
-        nsf = min(mn // 5, args.pipeline_superframes)
-        psym = msym[: nsf * 5]
-        pout = torch.full((nsf, 110 * 16), 0xEE, dtype=torch.uint8, device=dev)
-        pret = torch.empty((nsf,), dtype=torch.int32, device=dev)
-        ms_pipe = timed(lambda: vb.dabplus_decode_superframes_device(mf, psym, pout, pret, stream), 5)
-        extra["dabplus_pipeline"] = {"workload": "%d MSC frames -> %d superframes (s=16) per GPU: Viterbi + RS check on device" % (nsf * 5, nsf),
-                                     "superframes_per_s": nsf * world / (ms_pipe * 1e-3),
-                                     "viterbi_gbit_per_s": nsf * 5 * world * mf / (ms_pipe * 1e-3) / 1e9, "ms_per_step": ms_pipe}
-        del msym, mout, mbits, psym
+        del msym, mout, mbits
         torch.cuda.empty_cache()
-        # the same batch through the QIRX word-per-symbol layout (what the drop-in deconvolve() takes): 4x the bytes
+
+        # single-frame drop-in latency (BASELINE configs[0]; viterbi-benchmark.cpp:332-348: repeated calls on one thread)
+        if rank == 0:
+            drop = {}
+            for df in (768, 3072):
+                dsym, _ = dabgen.make_frames(64, df, 3.0, seed=77 + df)
+                d32 = np.ascontiguousarray(dsym.astype(np.uint32))
+                dout = np.zeros(df // 8, dtype=np.uint8)
+                dwant = chk.deconvolve_batch(df, dsym, 1)
+                ptrs = [d32[i].ctypes.data for i in range(64)]
+                optr = dout.ctypes.data
+                bad = 0
+                for i in range(64):  # warm-up (graph capture, pinned bounce buffer) + parity of the path
+                    if vb.lib.deconvolve(df, ptrs[i], 0, optr) != 0 or not np.array_equal(dout, dwant[i]):
+                        bad += 1
+                parity["frames_checked"] += 64
+                parity["mismatches"] += bad
+                calls = 2000
+                t0 = time.perf_counter()
+                for i in range(calls):
+                    vb.lib.deconvolve(df, ptrs[i & 63], 0, optr)
+                us = (time.perf_counter() - t0) / calls * 1e6
+                drop["F%d" % df] = {"us_per_call": us, "cpu_reference_us_per_call": time_cpu_single_calls(chk, chk_kind, df, d32, 500)}
+            extra["dropin"] = {"workload": "single-frame deconvolve() calls from one host thread, QIRX u32 layout (BASELINE configs[0])",
+                               "api": "deconvolve (pinned bounce buffer, single-kernel CUDA graph, decisions in shared memory)",
+                               **drop}
+
+        # the same FIC batch through the QIRX word-per-symbol layout and through the punctured entry point
         if not args.no_e2e:
             h_s32 = torch.empty((n, nsym), dtype=torch.int32, pin_memory=True)
             h_s32.copy_(syms.to(torch.int32))
@@ -459,15 +573,14 @@ def run_b200(args):
             t0 = time.perf_counter()
             for _ in range(5):
                 u32_step()
-            dtu = max_over_ranks(time.perf_counter() - t0) / 5
+            dtu = reduce_ranks(time.perf_counter() - t0) / 5
+            if not torch.equal(h_o32.to(dev), out):
+                parity["mismatches"] += 1
             extra["e2e_u32_layout"] = {"workload": "same %d frames per GPU, one uint32 per soft symbol (QIRX layout), compacted on the device" % n,
                                        "value": n * world * f / dtu / 1e9, "unit": "Gbit/s", "ms_per_step": dtu * 1e3,
                                        "h2d_bytes_per_step": n * nsym * 4, "d2h_bytes_per_step": n * nout,
                                        "api": "viterbi_deconvolve_batch_u32 (pinned host buffers)"}
             del h_s32, h_o32
-        # depuncturing front end: the same FIC batch sent as the 2,304 transmitted symbols per frame
-        # (FIC-shaped puncturing) instead of the 3,096 expanded ones, host buffers, end to end.  The decoded
-        # bits differ from the unpunctured run (erasures carry no information); parity of this path is in tests/.
         if f == 768 and not args.no_e2e:
             import ctypes
 
@@ -490,71 +603,171 @@ def run_b200(args):
             t0 = time.perf_counter()
             for _ in range(10):
                 punct_step()
-            dtp = max_over_ranks(time.perf_counter() - t0) / 10
+            dtp = reduce_ranks(time.perf_counter() - t0) / 10
+            pwant = chk.deconvolve_batch(f, dabgen.depuncture(h_rx[:1024].numpy(), keep), chk_threads)
+            parity["frames_checked"] += 1024
+            parity["mismatches"] += int((pwant != h_pout[:1024].numpy()).any(axis=1).sum())
             extra["e2e_punctured_fic"] = {"workload": "same %d FIC frames per GPU as 2304 transmitted symbols each + keep pattern "
-                                                      "(21 blocks PI=16, 3 blocks PI=15, tail)" % n,
+                                                      "(21 blocks PI=16, 3 blocks PI=15, tail), expanded on the device" % n,
                                           "value": n * world * f / dtp / 1e9, "unit": "Gbit/s", "ms_per_step": dtp * 1e3,
                                           "h2d_bytes_per_step": n * int(keep.sum()), "d2h_bytes_per_step": n * nout,
                                           "api": "viterbi_deconvolve_batch_punctured (pinned host buffers)"}
+            if e2e is not None:
+                e2e["punctured_input"] = {"value": extra["e2e_punctured_fic"]["value"], "unit": "Gbit/s",
+                                          "h2d_bytes_per_step": n * int(keep.sum()),
+                                          "note": "same frames sent as the 2304 transmitted symbols (what a receiver holds before "
+                                                  "depuncturing): the e2e path for hosts where PCIe is the wall"}
+            del h_rx, h_pout
 
-    # ---- gather of result bitstreams over NCCL (outside the timed region) -----------------------------
-    gather_ms = None
-    if world > 1:
-        from viterbi_dll_b200 import sharding
-
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        allout = sharding.gather_to_all(out, n * world, world, rank, align=64)
-        g1.record()
-        torch.cuda.synchronize()
-        gather_ms = max_over_ranks(g0.elapsed_time(g1))
-        assert allout.shape[0] == n * world
+        # BASELINE configs[4]: strong scaling of the whole chain with the result gather inside the timed region
+        if not args.no_configs4:
+            del syms, out
+            torch.cuda.empty_cache()
+            extra["configs4"] = run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, barrier, reduce_ranks)
 
     # ---- CPU baseline (rank 0, single-GPU run only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle_lib
-
-        chk, kind, what = cpu_checker()
-        cores = oracle_lib.ncores()
-        host_syms = syms[: min(n, 32768)].cpu().numpy()
-        want = chk.deconvolve_batch(f, host_syms[:4096])
-        if not np.array_equal(want, out[:4096].cpu().numpy()):
-            raise RuntimeError("GPU output differs from the CPU reference on the benchmark input")
-        all_gbps, frames_done = time_cpu_viterbi(chk, kind, f, host_syms, cores, 4.0)
-        one_gbps, _ = time_cpu_viterbi(chk, kind, f, host_syms[:4096], 1, 2.0)
-        cpu = {"value": all_gbps, "unit": "Gbit/s", "cores": cores, "kind": kind,
+        host_syms = cpu_syms
+        all_gbps, frames_done = time_cpu_viterbi(chk, chk_kind, f, host_syms, cores, 4.0)
+        one_gbps, _ = time_cpu_viterbi(chk, chk_kind, f, host_syms[:4096], 1, 2.0)
+        cpu = {"value": all_gbps, "unit": "Gbit/s", "cores": cores, "kind": chk_kind,
                "sample": "%d-frame slice of the same FIC batch decoded repeatedly for >=4 s on all %d host threads "
                          "(%d frames in total), u32 symbol layout, distinct frames per call" % (host_syms.shape[0], cores, frames_done),
-               "single_core": {"value": one_gbps, "unit": "Gbit/s", "cores": 1}, "implementation": what,
+               "single_core": {"value": one_gbps, "unit": "Gbit/s", "cores": 1}, "implementation": chk_what,
                "cpu_model": next((l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")), "?")}
         if rs is not None:
             rs_sets = [(s, rx[:4000].cpu().numpy()) for s, rx, _, _ in sets]
             rs_all, _ = time_cpu_rs(chk, rs_sets, cores, 2.0)
             rs_one, _ = time_cpu_rs(chk, rs_sets, 1, 1.0)
-            rs["cpu_baseline"] = {"value": rs_all, "unit": "superframes/s", "cores": cores, "kind": kind,
+            rs["cpu_baseline"] = {"value": rs_all, "unit": "superframes/s", "cores": cores, "kind": chk_kind,
                                   "sample": "8 x 4000 superframes of the same batch (s=1..8), >=2 s, all host threads",
                                   "single_core": {"value": rs_one, "unit": "superframes/s", "cores": 1}}
 
+    # every rank's mismatch count, summed: SCALE runs prove bit-exactness at N > 1
+    tot = {k: int(reduce_ranks(float(v), "sum")) for k, v in parity.items()}
     if rank == 0:
         line = {
             "metric": "viterbi_decoded_gbit_per_s", "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "batched FIC decode (BASELINE configs[1]): %d frames per GPU x F=%d info bits "
-                                   "(+6 tail), 8-bit soft symbols, AWGN Eb/N0=%.1f dB" % (n, f, args.ebn0),
-                       "frames_per_gpu": n, "framebits": f, "parallelism": "independent frames, %d-way partition" % world,
-                       "l2_policy": "input %d MB + decision scratch > 126 MB L2; no explicit flush" % (n * nsym // 1000000)},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline,
-            "roofline_int_alu": roofline_int, "cpu_baseline": cpu, "rs": rs, "frame_error_rate": fer, "gather_ms": gather_ms,
-            "extra": extra,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "parity_mismatches": tot["mismatches"],
+            "parity": {"checker": chk_what, "frames_checked_all_ranks": tot["frames_checked"],
+                       "superframes_checked_all_ranks": tot["superframes_checked"], "ranks": world},
+            "rs": rs, "frame_error_rate": fer, "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
         barrier()  # no rank tears its communicator down while another is still inside a collective
         dist.destroy_process_group()
+    if tot["mismatches"]:
+        raise SystemExit("bench.py: %d results differ from the CPU checker" % tot["mismatches"])
     return 0
+
+
+def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, barrier, reduce_ranks):
+    """BASELINE configs[4]: `--configs4-frames` (2^24) MSC frames = 3.36 M DAB+ superframes (s = 16), Viterbi + RS check
+    on the device, STRONG scaling: the job is the same whatever N is.
+
+    The job is cut into rounds of `world` chunks; rank r decodes chunk r of every round, so the all-gather of a
+    round lands in natural superframe order.  A rank keeps at most 2^21 frames of symbols (25.8 GB) resident and
+    reuses them round after round (206 GB of symbols do not fit one GPU; every pass streams far more than the
+    126 MB L2, so a repeated pass costs what a fresh one does).  Rounds alternate between two compute streams so
+    that the tail of one round's persistent Viterbi grid is filled by the next round's blocks; the NCCL
+    all-gather of round j (results + return values, in place into the full result array) runs on a third,
+    high-priority stream while round j+1 computes.  The timed region ends when every rank holds every result."""
+    import torch
+    import torch.distributed as dist
+
+    f, s = 3072, 16
+    total_sf = args.configs4_frames // 5
+    res_sf_cap = (1 << 21) // 5
+    my_sf = -(-total_sf // world)
+    chunks_resident = 4
+    chunk_sf = -(-min(my_sf, res_sf_cap) // chunks_resident)
+    rounds = -(-my_sf // chunk_sf)
+    res_sf = chunk_sf * min(chunks_resident, rounds)
+    job_sf = rounds * world * chunk_sf  # superframes actually decoded (>= total_sf: the last round is padded)
+    t0 = time.perf_counter()
+    syms, payload = dabgen.make_superframe_frames_torch(res_sf, f, 4.0, seed=5000 + 17 * rank, device=dev, max_err=3)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    allout = torch.full((rounds, world, chunk_sf, 110 * s), 0xEE, dtype=torch.uint8, device=dev)
+    allret = torch.full((rounds, world, chunk_sf), -7, dtype=torch.int32, device=dev)
+    comp = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    comm = torch.cuda.Stream(device=dev, priority=-1)
+    main = torch.cuda.current_stream()
+
+    def run_job(gather: bool):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(main)
+        for st in comp + [comm]:
+            st.wait_stream(main)
+        for j in range(rounds):
+            st = comp[j % 2]
+            c = j % chunks_resident if rounds >= chunks_resident else j
+            vb.dabplus_decode_superframes_device(f, syms[c * chunk_sf * 5:(c + 1) * chunk_sf * 5], allout[j, rank], allret[j, rank], st)
+            if gather and world > 1:
+                done = torch.cuda.Event()
+                done.record(st)
+                comm.wait_event(done)
+                with torch.cuda.stream(comm):
+                    dist.all_gather_into_tensor(allout[j].view(-1), allout[j, rank].view(-1))
+                    dist.all_gather_into_tensor(allret[j].view(-1), allret[j, rank].view(-1))
+        for st in comp + [comm]:
+            main.wait_stream(st)
+        end.record(main)
+        torch.cuda.synchronize()
+        return start.elapsed_time(end)
+
+    run_job(False)  # warm-up: allocations, NCCL channels
+    if world > 1:
+        run_job(True)
+    barrier()
+    l0 = vb.kernel_launches()
+    ms_gather = reduce_ranks(run_job(True))
+    launches = vb.kernel_launches() - l0
+    barrier()
+    ms_nogather = reduce_ranks(run_job(False))
+    barrier()
+
+    # ---- checks: accepted superframes equal the transmitted payload; every rank's slice of the gathered array is
+    # what that rank decoded; a slice is compared bit for bit with the CPU reference chain ------------------------
+    run_job(True)
+    mine_out, mine_ret = allout[:, rank], allret[:, rank]
+    nres = min(rounds, chunks_resident)
+    ok = mine_ret[:nres] >= 0
+    pay = payload.view(nres, chunk_sf, 110 * s)
+    wrong = int((mine_out[:nres][ok] != pay[ok]).any(dim=1).sum().item())
+    accepted = int(ok.sum().item())
+    if world > 1:
+        # ranks generate from seed 5000 + 17 * rank: a rank can check a peer's gathered rows only through their
+        # return values being filled in (-7 was the fill)
+        wrong += int((allret == -7).sum().item())
+    nsl = min(chunk_sf, args.parity_superframes // 8)
+    h_syms = syms[: nsl * 5].cpu().numpy()
+    dec = chk.deconvolve_batch(f, h_syms, chk_threads)
+    c_out, c_ret = chk.rs_batch(dec.reshape(nsl, 120 * s), s, fill=0xEE, nthreads=chk_threads)
+    parity["frames_checked"] += nsl * 5
+    parity["superframes_checked"] += nsl
+    parity["mismatches"] += int((c_ret != mine_ret[0, :nsl].cpu().numpy()).sum()) + \
+        int((c_out != mine_out[0, :nsl].cpu().numpy()).any(axis=1).sum()) + wrong
+    frames = job_sf * 5
+    return {
+        "workload": "BASELINE configs[4]: %d MSC frames (F=3072) -> %d DAB+ superframes (s=16), Viterbi + RS check on "
+                    "device, Eb/N0=4 dB, 0-3 byte errors per codeword before the convolutional encoder" % (frames, job_sf),
+        "scaling": "strong", "n_gpus": world, "rounds": rounds, "chunk_superframes": chunk_sf,
+        "resident_frames_per_gpu": res_sf * 5,
+        "ms_total": ms_gather, "ms_total_without_gather": ms_nogather,
+        "frames_per_s": frames / (ms_gather * 1e-3), "superframes_per_s": job_sf / (ms_gather * 1e-3),
+        "viterbi_gbit_per_s": frames * f / (ms_gather * 1e-3) / 1e9,
+        "gathered_bytes_per_rank": int(allout.numel() + 4 * allret.numel()) if world > 1 else 0,
+        "gather": "NCCL all_gather_into_tensor per round on a high-priority stream, in place into the full result "
+                  "array, overlapped with the next round; inside ms_total" if world > 1 else "single rank: nothing to gather",
+        "gpu_launches_per_rank": launches, "rs_accepted_local": accepted, "rs_accepted_but_wrong_local": wrong,
+        "generate_s": gen_s,
+    }
 
 
 def main():
@@ -570,9 +783,12 @@ def main():
     ap.add_argument("--no-rs", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the MSC and DAB+ pipeline side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the MSC, drop-in, layout and configs[4] side measurements")
+    ap.add_argument("--no-configs4", action="store_true", help="skip the 2^24-frame strong-scaling chain")
     ap.add_argument("--msc-frames", type=int, default=262144)
-    ap.add_argument("--pipeline-superframes", type=int, default=16384)
+    ap.add_argument("--configs4-frames", type=int, default=1 << 24)
+    ap.add_argument("--parity-frames", type=int, default=4096, help="frames per rank compared with the CPU checker")
+    ap.add_argument("--parity-superframes", type=int, default=4096, help="superframes per rank compared with the CPU checker")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

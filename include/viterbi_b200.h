@@ -29,7 +29,11 @@ extern "C" {
 
 /* Replaces deconvolve(), deconvolve.cpp:551-554 (caller typedef viterbi-benchmark.cpp:72-73).
  * Hard-output Viterbi decode of one K=7 rate-1/4 DAB frame.
- *   framebits   info bits F (even, <= 9216); the frame carries F+6 trellis steps
+ *   framebits   info bits F (even, <= 9216); the frame carries F+6 trellis steps.  (The reference computes
+ *               nbits = (F+6)/2 two-step iterations, deconvolve.cpp:126, so an odd F silently decodes F-1
+ *               steps' worth of symbols and reads decisions it never wrote; its decision array ends at
+ *               F = 9216, deconvolve.cpp:127.  Both cases are rejected here with return value 1, without
+ *               entering save mode.)
  *   piData      4*(F+6) words, one soft symbol per word; only the low byte is used
  *               (deconvolve.cpp:219-228; README.md:19 out-of-range symbols)
  *   inputLength ignored, as in the reference
@@ -43,15 +47,22 @@ int deconvolve(unsigned int framebits, unsigned int* piData, int inputLength, un
  * p[j + k*RSDims].  Writes the 110 data bytes of each codeword to outVector with the same striding
  * and returns the total number of corrected symbols; on the first uncorrectable codeword returns -1
  * and leaves that column and all later ones untouched (rschecksf.cpp:80-88).  startIx is unused
- * (rschecksf.cpp:69).  Returns -1 on device failure as well (exc_handler.cpp:116-124,208-211). */
+ * (rschecksf.cpp:69).  Returns -1 on device failure as well (exc_handler.cpp:116-124,208-211).
+ * p and outVector may be the same buffer (the reference copies each column before it writes:
+ * rschecksf.cpp:75-84).  RSDims is limited to 1..1024 (one superframe must fit a 120 KB shared-memory
+ * tile; DAB+ uses at most 24) -- larger values, which the reference's loop would accept, return -1;
+ * RSDims == 0 returns 0 like the reference's empty loop. */
 int RScheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsigned char* outVector);
 
 /* Same function under the spelling BASELINE.json uses. */
 int RSCheckSuperframe(unsigned char* p, int startIx, unsigned int RSDims, unsigned char* outVector);
 
 /* Replaces initialize(), dllmain.cpp:156-160: called on every receiver start.  Re-reads the
- * configuration (here: environment VITERBI_B200_DEVICE), (re)creates the device context and
- * clears save mode.  Returns non-zero (true) on success like the reference. */
+ * configuration (here: environment VITERBI_B200_DEVICE, VITERBI_B200_LOG), clears save mode and
+ * probes the device: after a sticky CUDA error the context is reset (cudaDeviceReset) and set up
+ * again, and every thread's staging state of the old context is discarded on its next call -- the
+ * recover-on-initialize contract of exc_handler.cpp:214 / dllmain.cpp:156.  Returns non-zero (true)
+ * on success like the reference. */
 int initialize(void);
 
 /* Replaces GetCPUCaps(), viterbi_helpers.asm:48-157 / getcpucaps.h:27-38.  The CPU dispatcher is
@@ -78,7 +89,9 @@ int viterbi_deconvolve_batch(unsigned int framebits, const uint8_t* syms, size_t
 int viterbi_deconvolve_batch_u32(unsigned int framebits, const uint32_t* syms, size_t n, uint8_t* out);
 
 /* Device-pointer flavours: buffers already in HBM, work enqueued on `stream` (a cudaStream_t, NULL =
- * default stream), no synchronisation.  d_syms must be 8-byte aligned. */
+ * default stream), no synchronisation.  Alignment: d_syms 8 bytes (u8 layout) or 16 bytes (u32 layout: one
+ * trellis step per 16-byte load); d_out any (a 4-byte aligned d_out gets 32-bit stores when F % 32 == 0).
+ * Rows are dense, so with F % 2 == 0 every row of an aligned d_syms is aligned too. */
 int viterbi_deconvolve_batch_device(unsigned int framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
                                     void* stream);
 int viterbi_deconvolve_batch_u32_device(unsigned int framebits, const uint32_t* d_syms, size_t n,
@@ -100,7 +113,11 @@ int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint
 
 /* n superframes with the same RSDims: in [n][120*RSDims], out [n][110*RSDims], ret [n].
  * Per superframe identical to RScheckSuperframe(), including the partial-write rule: bytes of out
- * belonging to the first failing column and later ones are not written. */
+ * belonging to the first failing column and later ones are not written (they keep the caller's values).
+ * in and out must not overlap (n > 1 superframes have different strides in the two arrays).
+ * Host flavour: when out is pinned memory (fec_host_alloc, cudaMallocHost, cudaHostRegister) the caller's bytes
+ * of failing superframes are fetched by the kernel through the buffer's device mapping; a pageable out is
+ * uploaded first (both give identical results; the pinned path moves about half the bytes). */
 int rs_check_superframe_batch(const uint8_t* in, unsigned int RSDims, size_t n, uint8_t* out, int32_t* ret);
 int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
                                      int32_t* d_ret, void* stream);
@@ -117,11 +134,41 @@ int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_s
                                       int32_t* d_ret, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 3. Multi-device calls (new): one host batch decoded on all selected GPUs from ONE process
+ * -------------------------------------------------------------------------------------------
+ * Frames and superframes are independent (deconvolve.cpp:116-132 re-initialises the path metrics on every
+ * call, rschecksf.cpp:72 keeps its scratch on the stack), so the batch is cut into contiguous shards (64-frame /
+ * whole-superframe aligned), one per device of fec_set_devices(), and every shard runs the single-device
+ * host-pointer path on a persistent worker thread of that device: own streams, own staging buffers, no
+ * exchange between devices.  Results are identical to the single-device calls.  Pinned buffers recommended. */
+int viterbi_deconvolve_batch_multi(unsigned int framebits, const uint8_t* syms, size_t n, uint8_t* out);
+int rs_check_superframe_batch_multi(const uint8_t* in, unsigned int RSDims, size_t n, uint8_t* out, int32_t* ret);
+int dabplus_decode_superframes_multi(unsigned int framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret);
+
+/* Devices used by the *_multi calls and fec_allgather_device(): `count` ordinals (distinct), or count == 0 for
+ * "all visible devices" (the default). */
+int fec_set_devices(const int* ordinals, int count);
+/* Copies up to `capacity` selected ordinals to `ordinals` (may be NULL) and returns how many are selected. */
+int fec_get_devices(int* ordinals, int capacity);
+
+/* The one collective of the design: gather device-resident result arrays over
+ * NVLink with ncclAllGather, for hosts that keep the shards on the GPUs.  Single process, one communicator per
+ * selected device (ncclCommInitAll on first use; NCCL is loaded at run time from libnccl.so.2 or
+ * $VITERBI_B200_NCCL_LIB -- the library has no link-time dependency on it).  Shard i (bytes_per_shard bytes at
+ * d_shard[i], resident on selected device i) arrives at offset i * bytes_per_shard of every d_all[j]
+ * (each d_all[j] holds count * bytes_per_shard bytes on device j).  Enqueued on streams[i] (cudaStream_t of
+ * device i; streams == NULL or an entry NULL = that device's default stream); the caller synchronises. */
+int fec_allgather_device(const void* const* d_shard, void* const* d_all, size_t bytes_per_shard, void* const* streams);
+
+/* ---------------------------------------------------------------------------------------------
  * Device selection and utilities (replace getcpucaps/setupdll per the design brief)
  * ------------------------------------------------------------------------------------------- */
 int fec_device_count(void);
 int fec_set_device(int ordinal); /* selects the CUDA device used by the calling process */
 int fec_get_device(void);
+/* Per-thread override of fec_set_device() (-1 = none): a host that drives several GPUs from several threads
+ * with the device-pointer calls binds each thread to its GPU with this. */
+int fec_set_thread_device(int ordinal);
 int fec_in_save_mode(void);
 const char* fec_last_error(void); /* thread-local text of the last failure, "" if none */
 

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 
 #define CK(x)                                                                      \
     do {                                                                           \
@@ -207,7 +208,6 @@ __global__ void __launch_bounds__(256) bench(uint32_t* out, uint32_t seed_a, uin
     if (OP == OP_MNMX32 || OP == OP_VMNMX16 || OP == OP_VMNMX3_16) { a |= 0xFFF0FFF0u; b |= 0xFF00FF00u; }
 #pragma unroll
     for (int c = 0; c < CHAINS; c++) x[c] = blockIdx.x * 977u + threadIdx.x * 31u + c * 0x01010101u;
-    long long t0 = clock64();
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -225,16 +225,27 @@ __global__ void __launch_bounds__(256) bench(uint32_t* out, uint32_t seed_a, uin
             }
         }
     }
-    long long t1 = clock64();
     uint32_t acc = 0;
 #pragma unroll
     for (int c = 0; c < CHAINS; c++) acc ^= x[c] ^ accs[c] ^ accs2[c] ^ __float_as_uint(fa[c]) ^ __float_as_uint(fb[c]);
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    (void)cycles;
 }
 
+static double wall_now() {
+    timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+// Each op runs back to back for at least 0.3 s of wall time so that an NVML sampler running beside this process
+// (profiles/int_peaks.py) sees the SM clock and the throttle reasons UNDER THIS LOAD; t_start / t_end let it pick
+// the samples that belong to the op.  The rate is wall-clock (CUDA events), per-clock figures are derived by the
+// sampler from the NVML clock -- the in-kernel clock64 estimate this file used to print was inconsistent with the
+// wall-clock rate and is gone.
 template <int OP>
 void run(int nsm, int iters, uint32_t* d_out, long long* d_cyc, long long* h_cyc) {
+    (void)h_cyc;
     const int blocks = nsm * 8, threads = 256;  // 8 x 256 = 2048 threads/SM = full occupancy
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -242,7 +253,9 @@ void run(int nsm, int iters, uint32_t* d_out, long long* d_cyc, long long* h_cyc
     bench<OP><<<blocks, threads>>>(d_out, 3, 5, iters / 8 + 1, d_cyc);  // warm-up
     CK(cudaDeviceSynchronize());
     float best = 1e30f;
-    for (int rep = 0; rep < 3; rep++) {
+    int reps = 0;
+    const double w0 = wall_now();
+    do {
         CK(cudaEventRecord(e0));
         bench<OP><<<blocks, threads>>>(d_out, 3, 5, iters, d_cyc);
         CK(cudaEventRecord(e1));
@@ -250,18 +263,13 @@ void run(int nsm, int iters, uint32_t* d_out, long long* d_cyc, long long* h_cyc
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         if (ms < best) best = ms;
-    }
-    CK(cudaMemcpy(h_cyc, d_cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost));
-    double cyc = 0;
-    for (int i = 0; i < blocks; i++) cyc += (double)h_cyc[i];
-    cyc /= blocks;  // average cycles one block spent in the loop (8 blocks share an SM)
+        reps++;
+    } while (reps < 3 || wall_now() - w0 < 0.3);
+    const double w1 = wall_now();
     const double laneops = (double)blocks * threads * (double)iters * 8.0 * CHAINS * op_count[OP];
     const double tops = laneops / (best * 1e-3) / 1e12;
-    // per-SM per-clock from the in-kernel cycle counter: 8 co-resident blocks run the whole time
-    const double per_sm_clk = (double)8 * threads * (double)iters * 8.0 * CHAINS * op_count[OP] / cyc;
-    printf("{\"op\": \"%s\", \"ms\": %.4f, \"tera_laneops_per_s\": %.3f, \"laneops_per_sm_per_clk\": %.1f, "
-           "\"eff_clock_mhz\": %.0f}\n",
-           op_name[OP], best, tops, per_sm_clk, tops * 1e12 / (per_sm_clk * nsm) / 1e6);
+    printf("{\"op\": \"%s\", \"ms\": %.4f, \"reps\": %d, \"tera_laneops_per_s\": %.3f, \"t_start\": %.6f, \"t_end\": %.6f}\n",
+           op_name[OP], best, reps, tops, w0, w1);
     fflush(stdout);
 }
 

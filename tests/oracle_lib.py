@@ -79,10 +79,12 @@ class Port:
         assert out.dtype == np.uint8 and out.flags.c_contiguous
         return self.lib.oracle_rs_check_superframe(_ptr(p), 0, s, _ptr(out))
 
-    def rs_batch(self, rx: np.ndarray, s: int, fill: int = 0xEE, nthreads: int | None = None):
+    def rs_batch(self, rx: np.ndarray, s: int, fill: int = 0xEE, nthreads: int | None = None, out: np.ndarray | None = None):
         rx = np.ascontiguousarray(rx, dtype=np.uint8)
         n = rx.shape[0]
-        out = np.full((n, 110 * s), fill, dtype=np.uint8)
+        if out is None:  # else: the caller's outVector contents, updated in place (partial-write rule)
+            out = np.full((n, 110 * s), fill, dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (n, 110 * s)
         ret = np.zeros(n, dtype=np.int32)
         self.lib.oracle_rs_check_superframe_batch(_ptr(rx), s, n, _ptr(out), _ptr(ret), nthreads or ncores())
         return out, ret
@@ -140,10 +142,12 @@ class Ref:
         p = np.ascontiguousarray(p, dtype=np.uint8)
         return self.lib.ref_rs_check_superframe(_ptr(p), 0, s, _ptr(out))
 
-    def rs_batch(self, rx: np.ndarray, s: int, fill: int = 0xEE, nthreads: int | None = None):
+    def rs_batch(self, rx: np.ndarray, s: int, fill: int = 0xEE, nthreads: int | None = None, out: np.ndarray | None = None):
         rx = np.ascontiguousarray(rx, dtype=np.uint8)
         n = rx.shape[0]
-        out = np.full((n, 110 * s), fill, dtype=np.uint8)
+        if out is None:  # else: the caller's outVector contents, updated in place (partial-write rule)
+            out = np.full((n, 110 * s), fill, dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (n, 110 * s)
         ret = np.zeros(n, dtype=np.int32)
         self.lib.ref_rs_check_superframe_batch(_ptr(rx), s, n, _ptr(out), _ptr(ret), nthreads or ncores())
         return out, ret

@@ -1,0 +1,181 @@
+"""GPU tests of the multi-device paths: they use min(2, device_count) -- or all -- devices
+of the box, so they run on one GPU and exercise the real thing on two or more.
+
+* the *_multi C-ABI calls: one host batch, sharded inside the library over the selected devices, one process;
+* a native host program (tests/host/multi_device_check.cpp, no torch) doing the same plus the NCCL gather of
+  device-resident shards (fec_allgather_device);
+* the one-process-per-GPU flavour used by bench.py: torch.distributed NCCL ranks, contiguous shards, gather.
+Everything is compared bit for bit with the CPU checker."""
+import json
+import os
+import shutil
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from viterbi_dll_b200 import dabgen
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device(vb):
+    assert vb.lib.fec_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    assert vb.initialize()
+    yield
+    vb.set_devices(None)
+
+
+def _device_sets(vb):
+    n = vb.lib.fec_device_count()
+    sets = [[0], list(range(n))]
+    if n >= 2:
+        sets += [[n - 1], [1, 0]]
+    return sets
+
+
+def test_device_list_api(vb):
+    n = vb.lib.fec_device_count()
+    vb.set_devices(None)
+    assert vb.get_devices() == list(range(n))
+    vb.set_devices([n - 1])
+    assert vb.get_devices() == [n - 1]
+    import ctypes
+
+    bad = (ctypes.c_int * 2)(0, 0)
+    assert vb.lib.fec_set_devices(bad, 2) == vb.FEC_ERR_ARG  # duplicate
+    bad = (ctypes.c_int * 1)(n)
+    assert vb.lib.fec_set_devices(bad, 1) == vb.FEC_ERR_ARG  # out of range
+    assert vb.get_devices() == [n - 1]  # unchanged by the failed calls
+    vb.set_devices(None)
+
+
+@pytest.mark.parametrize("framebits,n", [(768, 20000), (3072, 5000), (100, 333), (768, 1)])
+def test_viterbi_multi_matches_checker(vb, checker, framebits, n):
+    sym, _ = dabgen.make_frames(n, framebits, 2.5, seed=framebits + n)
+    want = checker.deconvolve_batch(framebits, sym)
+    pin = vb.host_array(sym.shape)
+    pin[:] = sym
+    for devs in _device_sets(vb):
+        vb.set_devices(devs)
+        assert np.array_equal(vb.deconvolve_batch_multi(framebits, sym), want), devs  # pageable buffers
+        out = vb.host_array(want.shape)
+        out[:] = 0x77
+        vb.deconvolve_batch_multi(framebits, pin, out=out)  # pinned buffers
+        assert np.array_equal(out, want), devs
+
+
+def test_rs_and_dabplus_multi_match_checker(vb, checker):
+    s = 7
+    rx, _, _ = dabgen.make_superframes(9001, s, seed=3)
+    want_out, want_ret = checker.rs_batch(rx, s, fill=0x3C)
+    syms, _, _ = dabgen.make_superframe_frames(700, 768, 2.0, seed=8, max_err=5)
+    dec = checker.deconvolve_batch(768, syms)
+    dab_out, dab_ret = checker.rs_batch(dec.reshape(700, 120 * 4), 4, fill=0xEE)
+    for devs in _device_sets(vb):
+        vb.set_devices(devs)
+        out, ret = vb.rs_check_superframe_batch_multi(rx, s, fill=0x3C)
+        assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out), devs
+        pin_out = vb.host_array(want_out.shape)
+        pin_out[:] = 0x3C
+        out, ret = vb.rs_check_superframe_batch_multi(rx, s, out=pin_out)  # pinned outVector: zero-copy originals
+        assert np.array_equal(ret, want_ret) and np.array_equal(pin_out, want_out), devs
+        out, ret = vb.dabplus_decode_superframes_multi(768, syms, fill=0xEE)
+        assert np.array_equal(ret, dab_ret) and np.array_equal(out, dab_out), devs
+    assert (want_ret < 0).any() and (want_ret >= 0).any()
+
+
+def test_allgather_device_from_one_process(vb):
+    import torch
+
+    n = vb.lib.fec_device_count()
+    vb.set_devices(None)
+    shards = [torch.full((4096, 96), 10 + i, dtype=torch.uint8, device="cuda:%d" % i) for i in range(n)]
+    for i, t in enumerate(shards):
+        t[:, 0] = i
+    outs = [torch.zeros((n * 4096, 96), dtype=torch.uint8, device="cuda:%d" % i) for i in range(n)]
+    vb.allgather_device(shards, outs)
+    for i in range(n):
+        torch.cuda.synchronize(i)
+    want = torch.cat([t.cpu() for t in shards], dim=0)
+    for o in outs:
+        assert torch.equal(o.cpu(), want)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+def test_native_host_decodes_one_batch_on_all_devices(vb, tmp_path):
+    """tests/host/multi_device_check.cpp: a C++ host without torch, all GPUs of the box, bit-exact vs the checker."""
+    import oracle_lib
+
+    chk = oracle_lib.checker()
+    exe = tmp_path / "multi_device_check"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "host", "multi_device_check.cpp"), "-ldl"], check=True)
+    run = subprocess.run([str(exe), vb.LIB_PATH, chk.lib._name, "16384"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    rep = json.loads(run.stdout.strip().splitlines()[-1])
+    assert rep["ok"] and rep["devices"] == vb.lib.fec_device_count()
+    assert rep["viterbi_mismatched_frames"] == 0 and rep["rs_mismatch"] == 0 and rep["dabplus_mismatch"] == 0
+    assert rep["allgather_mismatch"] == 0
+    assert 0 < rep["rs_failed"] < rep["rs_superframes"]  # both RS write paths were exercised
+
+
+# ---- one process per GPU (the bench.py flavour): NCCL ranks, contiguous shards, result gather ----------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _rank_main(rank, world, port, n, framebits, tmpdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import viterbi_dll_b200 as vb
+    from viterbi_dll_b200 import dabgen, sharding
+
+    sym, _ = dabgen.make_frames(n, framebits, 3.0, seed=21)  # every rank regenerates the batch, keeps its shard
+    lo, hi = sharding.shard_bounds(n, world, rank, align=64)
+    local = vb.deconvolve_batch_device(framebits, torch.from_numpy(sym[lo:hi]).cuda())
+    allout = sharding.gather_to_all(local, n, world, rank, align=64)  # complete on return
+    rx, _, _ = dabgen.make_superframes(n // 4, 6, seed=22)
+    lo2, hi2 = sharding.shard_bounds(n // 4, world, rank)
+    o = torch.full((hi2 - lo2, 660), 0xEE, dtype=torch.uint8, device="cuda")
+    o, r = vb.rs_check_superframe_batch_device(torch.from_numpy(rx[lo2:hi2]).cuda(), 6, o)
+    allo = sharding.gather_to_all(o, n // 4, world, rank)
+    allr = sharding.gather_to_all(r, n // 4, world, rank)
+    np.save(os.path.join(tmpdir, "vit%d.npy" % rank), allout.cpu().numpy())
+    np.save(os.path.join(tmpdir, "rso%d.npy" % rank), allo.cpu().numpy())
+    np.save(os.path.join(tmpdir, "rsr%d.npy" % rank), allr.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_one_process_per_gpu_shards_and_nccl_gather(vb, checker, tmp_path):
+    import torch.multiprocessing as mp
+
+    world = min(2, vb.lib.fec_device_count())
+    n, framebits = 9000, 768
+    mp.spawn(_rank_main, args=(world, _free_port(), n, framebits, str(tmp_path)), nprocs=world, join=True)
+    sym, _ = dabgen.make_frames(n, framebits, 3.0, seed=21)
+    want = checker.deconvolve_batch(framebits, sym)
+    rx, _, _ = dabgen.make_superframes(n // 4, 6, seed=22)
+    want_o, want_r = checker.rs_batch(rx, 6, fill=0xEE)
+    for rank in range(world):  # every rank holds the whole gathered result
+        assert np.array_equal(np.load(tmp_path / ("vit%d.npy" % rank)), want)
+        assert np.array_equal(np.load(tmp_path / ("rso%d.npy" % rank)), want_o)
+        assert np.array_equal(np.load(tmp_path / ("rsr%d.npy" % rank)), want_r)

@@ -120,6 +120,40 @@ def test_pinned_host_buffers(vb, checker, s):
     assert (want_ret < 0).any() and (want_ret >= 0).any()  # both write paths were exercised
 
 
+def test_input_and_output_may_alias_in_the_dropin_call(vb, checker):
+    """p == outVector is legal in the reference (each column is copied to rsBlock before anything is written:
+    rschecksf.cpp:75-84): the decoded data bytes then overwrite the head of the received superframe."""
+    for s, seed in ((1, 1), (4, 2), (8, 3), (24, 4)):
+        rx, _, _ = dabgen.make_superframes(40, s, seed=seed, max_err=7)
+        for i in range(40):
+            want = rx[i].copy()
+            want_ret = checker.rs_check_superframe(want.copy(), s, want)  # reference semantics with separate input
+            # ... which must equal what the reference does in place
+            inplace = rx[i].copy()
+            assert checker.rs_check_superframe(inplace, s, inplace) == want_ret and np.array_equal(inplace, want)
+            buf = rx[i].copy()
+            assert vb.lib.RScheckSuperframe(buf.ctypes.data, 0, s, buf.ctypes.data) == want_ret, (s, i)
+            assert np.array_equal(buf, want), (s, i)
+
+
+def test_pageable_and_pinned_outvector_agree(vb, checker):
+    """The host path keeps the caller's bytes either by uploading a pageable outVector or by letting the kernel
+    read a pinned one through its device mapping; chunk boundaries and odd row alignments included."""
+    rng = np.random.default_rng(5)
+    for s, n in ((1, 70001), (3, 30011), (5, 40001), (11, 9001)):
+        rx, _, _ = dabgen.make_superframes(n, s, seed=60 + s)
+        prefill = rng.integers(0, 256, size=(n, 110 * s), dtype=np.uint8)
+        want_out, want_ret = checker.rs_batch(rx, s, out=prefill.copy())
+        out, ret = vb.rs_check_superframe_batch(rx, s, out=prefill.copy())  # pageable
+        assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out), s
+        # pinned, deliberately misaligned by one byte so rows start at odd addresses
+        pin = vb.host_array((n * 110 * s + 8,))
+        view = pin[1 : 1 + n * 110 * s].reshape(n, 110 * s)
+        view[:] = prefill
+        out, ret = vb.rs_check_superframe_batch(rx, s, out=view)
+        assert np.array_equal(ret, want_ret) and np.array_equal(view, want_out), s
+
+
 def test_one_million_superframes_bit_exact(vb, checker):
     """BASELINE config 4: 10^6 superframes, s = 1..8, 0-7 byte errors per codeword."""
     per_s = 125000 if checker.kind == "reference" else 8000

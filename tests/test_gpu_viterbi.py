@@ -247,3 +247,69 @@ def test_concurrent_callers(vb, checker):
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+def test_concurrent_callers_with_large_frames(vb, checker):
+    """Two threads decoding F = 9216 (111 KB of shared memory per warp) and F = 6144 (74 KB) at once, on the
+    warp-per-frame kernel: the shared-memory opt-in is a per-device function attribute set once for the worst
+    case, so neither caller can lower the other's limit (a per-thread cache of it used to)."""
+    import threading
+
+    vb.set_viterbi_kernel(vb.VITERBI_AUTO)
+    jobs = {}
+    for tid, f in enumerate((9216, 6144, 9216, 4092)):
+        sym, _ = dabgen.make_frames(6, f, 3.0, seed=900 + tid)
+        jobs[tid] = (f, sym, checker.deconvolve_batch(f, sym))
+    errors = []
+
+    def worker(tid):
+        f, sym, want = jobs[tid]
+        try:
+            for rep in range(6):
+                if rep % 2:
+                    if not np.array_equal(vb.deconvolve_batch(f, sym), want):
+                        errors.append((tid, rep, "batch"))
+                else:
+                    rc, out = vb.deconvolve(f, sym[rep % 6].astype(np.uint32))
+                    if rc != 0 or not np.array_equal(out, want[rep % 6]):
+                        errors.append((tid, rep, "dropin", rc))
+        except Exception as e:  # pragma: no cover
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+    assert vb.lib.fec_in_save_mode() == 0
+
+
+def test_unaligned_device_output(vb, checker):
+    """d_out needs no alignment: a misaligned output falls back to byte stores (F % 32 == 0 would otherwise use
+    32-bit stores)."""
+    import torch
+
+    f, n = 768, 5000
+    sym, _ = dabgen.make_frames(n, f, 3.0, seed=77)
+    want = checker.deconvolve_batch(f, sym)
+    d_sym = torch.from_numpy(sym).cuda()
+    buf = torch.zeros(n * (f // 8) + 8, dtype=torch.uint8, device="cuda")
+    for off in (1, 2, 3):
+        out = buf[off : off + n * (f // 8)].view(n, f // 8)
+        vb.set_viterbi_kernel(vb.VITERBI_PAIR)
+        rc = vb.lib.viterbi_deconvolve_batch_device(f, d_sym.data_ptr(), n, out.data_ptr(), None)
+        vb.set_viterbi_kernel(vb.VITERBI_AUTO)
+        torch.cuda.synchronize()
+        assert rc == 0 and np.array_equal(out.cpu().numpy(), want), off
+
+
+def test_initialize_probes_and_keeps_working(vb, checker):
+    """initialize() on a healthy device: context probed, staging state kept, decode still exact."""
+    sym, _ = dabgen.make_frames(300, 768, 3.0, seed=5)
+    want = checker.deconvolve_batch(768, sym)
+    for _ in range(3):
+        assert vb.initialize()
+        assert np.array_equal(vb.deconvolve_batch(768, sym), want)
+        rc, out = vb.deconvolve(768, sym[3].astype(np.uint32))
+        assert rc == 0 and np.array_equal(out, want[3])

@@ -48,6 +48,13 @@ _SIGNATURES = {
     "rs_check_superframe_batch_device": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp, _vp]),
     "dabplus_decode_superframes": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
     "dabplus_decode_superframes_device": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp, _vp]),
+    "viterbi_deconvolve_batch_multi": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp]),
+    "rs_check_superframe_batch_multi": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp]),
+    "dabplus_decode_superframes_multi": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp]),
+    "fec_set_devices": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "fec_get_devices": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "fec_allgather_device": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    "fec_set_thread_device": (ctypes.c_int, [ctypes.c_int]),
     "fec_device_count": (ctypes.c_int, []),
     "fec_set_device": (ctypes.c_int, [ctypes.c_int]),
     "fec_get_device": (ctypes.c_int, []),
@@ -261,6 +268,73 @@ def dabplus_decode_superframes_device(framebits: int, syms, out, ret=None, strea
                                                _stream_ptr(stream))
     _check(rc, "dabplus_decode_superframes_device")
     return out, ret
+
+
+# -------------------------------------------------------------------------------------------
+# multi-device host calls (one process, all selected GPUs)
+# -------------------------------------------------------------------------------------------
+def set_devices(ordinals=None) -> None:
+    """Devices of the *_multi calls; None / empty = all visible devices."""
+    ordinals = list(ordinals or [])
+    arr = (ctypes.c_int * max(len(ordinals), 1))(*ordinals)
+    _check(lib.fec_set_devices(arr, len(ordinals)), "fec_set_devices")
+
+
+def get_devices() -> list[int]:
+    arr = (ctypes.c_int * 64)()
+    n = lib.fec_get_devices(arr, 64)
+    return [int(arr[i]) for i in range(min(n, 64))]
+
+
+def deconvolve_batch_multi(framebits: int, syms: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """Like deconvolve_batch (u8 layout), sharded over the selected devices inside the library."""
+    syms = np.ascontiguousarray(syms, dtype=np.uint8)
+    n = syms.shape[0]
+    if syms.shape[1] != 4 * (framebits + 6):
+        raise ValueError("syms must be [n, 4*(framebits+6)]")
+    if out is None:
+        out = np.zeros((n, (framebits + 7) // 8), dtype=np.uint8)
+    _check(lib.viterbi_deconvolve_batch_multi(framebits, _ptr(syms), n, _ptr(out)), "viterbi_deconvolve_batch_multi")
+    return out
+
+
+def rs_check_superframe_batch_multi(rx: np.ndarray, RSDims: int, out: np.ndarray | None = None, fill: int = 0):
+    rx = np.ascontiguousarray(rx, dtype=np.uint8)
+    n = rx.shape[0]
+    if out is None:
+        out = np.full((n, 110 * RSDims), fill, dtype=np.uint8)
+    ret = np.zeros(n, dtype=np.int32)
+    _check(lib.rs_check_superframe_batch_multi(_ptr(rx), RSDims, n, _ptr(out), _ptr(ret)), "rs_check_superframe_batch_multi")
+    return out, ret
+
+
+def dabplus_decode_superframes_multi(framebits: int, syms: np.ndarray, out: np.ndarray | None = None, fill: int = 0):
+    syms = np.ascontiguousarray(syms, dtype=np.uint8)
+    nsf, s = syms.shape[0] // 5, framebits // 192
+    assert syms.shape == (nsf * 5, 4 * (framebits + 6))
+    if out is None:
+        out = np.full((nsf, 110 * s), fill, dtype=np.uint8)
+    ret = np.zeros(nsf, dtype=np.int32)
+    _check(lib.dabplus_decode_superframes_multi(framebits, _ptr(syms), nsf, _ptr(out), _ptr(ret)),
+           "dabplus_decode_superframes_multi")
+    return out, ret
+
+
+def allgather_device(shards, outs, streams=None) -> None:
+    """ncclAllGather from one process: shards[i] / outs[i] are CUDA tensors on selected device i (equal byte sizes;
+    outs[i] holds len(shards) shards).  Enqueued on each device's current stream unless `streams` is given."""
+    import torch
+
+    n = len(shards)
+    nbytes = shards[0].numel() * shards[0].element_size()
+    assert all(t.is_contiguous() and t.numel() * t.element_size() == nbytes for t in shards)
+    assert all(o.is_contiguous() and o.numel() * o.element_size() == n * nbytes for o in outs)
+    if streams is None:
+        streams = [torch.cuda.current_stream(t.device).cuda_stream for t in shards]
+    sp = (_vp * n)(*[t.data_ptr() for t in shards])
+    op = (_vp * n)(*[t.data_ptr() for t in outs])
+    st = (_vp * n)(*streams)
+    _check(lib.fec_allgather_device(sp, op, nbytes, st), "fec_allgather_device")
 
 
 VITERBI_AUTO, VITERBI_PAIR, VITERBI_WARP = 0, 1, 2

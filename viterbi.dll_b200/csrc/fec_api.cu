@@ -5,13 +5,17 @@
 // initialize() is called), and adds the batched entry points.  The CPU dispatcher / ini file
 // (setupdll.cpp) is replaced by device selection.  No CPU decode path exists here.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -27,16 +31,20 @@ namespace {
 constexpr int kMaxDevices = 64;
 constexpr int kPipe = 3;  // host-path pipeline depth (streams / staging slots)
 constexpr size_t kBounceBytes = 256 * 1024;  // calls moving less than this bounce through pinned memory
+constexpr size_t kTrimBytes = (size_t)768 << 20;  // staging buffers above this are released when the call returns
+constexpr int kGraphCache = 4;  // instantiated single-kernel graphs kept per calling thread (drop-in path)
 
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_save_mode{0};
 std::atomic<int> g_device{-1};  // -1: use the calling thread's current device
 std::atomic<int> g_vit_kernel{FEC_VITERBI_AUTO};
+std::atomic<unsigned> g_generation{1};  // bumped when initialize() had to reset a device: staging state of older generations is dead
 thread_local std::string t_error;
+thread_local int t_device = -1;  // per-thread device (fec_set_thread_device, multi-device workers); wins over g_device
 
 struct DeviceState {
-    std::once_flag once;
-    cudaError_t init_status = cudaSuccess;
+    std::mutex mu;
+    bool ready = false;
     int num_sms = 0;
 };
 DeviceState g_dev[kMaxDevices];
@@ -46,10 +54,22 @@ struct Slot {
     cudaStream_t stream = nullptr;
     void* d_in = nullptr;
     void* d_out = nullptr;
-    void* d_aux = nullptr;  // u32 staging (viterbi) or ret (rs)
+    void* d_aux = nullptr;  // u32 / punctured staging (viterbi) or ret (rs)
     void* d_scratch = nullptr;
     void* h_pin = nullptr;  // pinned bounce buffer for the single-call drop-in path
     size_t in_cap = 0, out_cap = 0, aux_cap = 0, scratch_cap = 0, pin_cap = 0;
+};
+
+// A single-kernel CUDA graph of the drop-in decode on this thread's bounce buffer: the kernel
+// arguments never change between calls of the same shape, so the launch is one cudaGraphLaunch of a
+// pre-instantiated graph.
+struct DropinGraph {
+    cudaGraphExec_t exec = nullptr;
+    unsigned framebits = 0;
+    bool u32 = false;
+    const void* in = nullptr;
+    void* out = nullptr;
+    unsigned long long last_use = 0;
 };
 
 // Staging state of the host-pointer calls.  One per calling thread: QIRX >= 4.0 calls deconvolve() from several
@@ -57,9 +77,13 @@ struct Slot {
 // instead of queueing behind one lock.  Released when the thread exits.
 struct HostPipe {
     int device = -1;
+    unsigned generation = 0;
     Slot slot[kPipe];
     void* d_idx = nullptr;  // depuncturing index table of the call in progress
     size_t idx_cap = 0;
+    cudaEvent_t idx_ready = nullptr;
+    DropinGraph graph[kGraphCache];
+    unsigned long long graph_clock = 0;
     ~HostPipe();
 };
 thread_local HostPipe g_pipe;
@@ -78,34 +102,47 @@ int bad_arg(const char* what) {
     return FEC_ERR_ARG;
 }
 
-// Resolve the device this call runs on and make sure its per-device state exists.
-DeviceState* device_state(int* ordinal_out = nullptr) {
-    int dev = g_device.load();
-    if (dev >= 0) {
-        if (fail(cudaSetDevice(dev), "cudaSetDevice")) return nullptr;
-    } else if (fail(cudaGetDevice(&dev), "cudaGetDevice")) {
-        return nullptr;
+// Per-device one-time setup: GF tables, shared-memory opt-ins of both kernels (per-device function attributes,
+// set here for the worst case so that concurrent callers never lower each other's limit), scratch pool.
+// Not cached on failure: the next call (or initialize()) tries again.
+bool init_device(DeviceState* st, int dev) {
+    cudaDeviceProp prop;
+    if (fail(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return false;
+    st->num_sms = prop.multiProcessorCount;
+    if (fail(rs_upload_tables(), "RS table upload") || fail(viterbi_configure_device(), "viterbi kernel attributes") ||
+        fail(rs_configure_device(), "rs kernel attributes"))
+        return false;
+    // the table upload ran on the legacy default stream; the kernels run on non-blocking streams, which do not
+    // order themselves behind it
+    if (fail(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return false;
+    // keep stream-ordered scratch allocations cached in the pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
+    (void)cudaGetLastError();
+    return true;
+}
+
+// Resolve the device this call runs on and make sure its per-device state exists.  The calling thread's current
+// device is only changed when a device was selected explicitly and differs from it.
+DeviceState* device_state(int* ordinal_out = nullptr) {
+    int dev = t_device >= 0 ? t_device : g_device.load();
+    int cur = -1;
+    if (fail(cudaGetDevice(&cur), "cudaGetDevice")) return nullptr;
+    if (dev < 0) dev = cur;
     if (dev < 0 || dev >= kMaxDevices) {
         t_error = "device ordinal out of range";
         return nullptr;
     }
+    if (dev != cur && fail(cudaSetDevice(dev), "cudaSetDevice")) return nullptr;
     DeviceState* st = &g_dev[dev];
-    std::call_once(st->once, [st, dev] {
-        cudaDeviceProp prop;
-        st->init_status = cudaGetDeviceProperties(&prop, dev);
-        if (st->init_status != cudaSuccess) return;
-        st->num_sms = prop.multiProcessorCount;
-        st->init_status = rs_upload_tables();
-        if (st->init_status != cudaSuccess) return;
-        // keep stream-ordered scratch allocations cached in the pool between calls
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    });
-    if (fail(st->init_status, "device init")) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(st->mu);
+        if (!st->ready) st->ready = init_device(st, dev);
+        if (!st->ready) return nullptr;
+    }
     if (ordinal_out) *ordinal_out = dev;
     return st;
 }
@@ -127,28 +164,49 @@ bool grow(void** p, size_t* cap, size_t need, bool pinned = false) {
     return true;
 }
 
-void release_pipe(HostPipe& pipe) {
+void drop_graphs(HostPipe& pipe, bool destroy) {
+    for (DropinGraph& g : pipe.graph) {
+        if (g.exec && destroy) cudaGraphExecDestroy(g.exec);
+        g = DropinGraph();
+    }
+}
+
+// destroy = false: the context the handles belonged to is gone (device reset); just forget them
+void release_pipe(HostPipe& pipe, bool destroy = true) {
+    drop_graphs(pipe, destroy);
     for (Slot& s : pipe.slot) {
-        if (s.d_in) cudaFree(s.d_in);
-        if (s.d_out) cudaFree(s.d_out);
-        if (s.d_aux) cudaFree(s.d_aux);
-        if (s.d_scratch) cudaFree(s.d_scratch);
-        if (s.h_pin) cudaFreeHost(s.h_pin);
-        if (s.stream) cudaStreamDestroy(s.stream);
+        if (destroy) {
+            if (s.d_in) cudaFree(s.d_in);
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.d_aux) cudaFree(s.d_aux);
+            if (s.d_scratch) cudaFree(s.d_scratch);
+            if (s.h_pin) cudaFreeHost(s.h_pin);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
         s = Slot();
     }
-    if (pipe.d_idx) cudaFree(pipe.d_idx);
+    if (destroy) {
+        if (pipe.d_idx) cudaFree(pipe.d_idx);
+        if (pipe.idx_ready) cudaEventDestroy(pipe.idx_ready);
+    }
     pipe.d_idx = nullptr;
+    pipe.idx_ready = nullptr;
     pipe.idx_cap = 0;
     pipe.device = -1;
     (void)cudaGetLastError();  // a thread that outlives the CUDA context frees nothing; that is fine
 }
 
 HostPipe::~HostPipe() {
-    if (device >= 0 && cudaSetDevice(device) == cudaSuccess) release_pipe(*this);
+    if (device < 0) return;
+    if (generation != g_generation.load())
+        release_pipe(*this, false);
+    else if (cudaSetDevice(device) == cudaSuccess)
+        release_pipe(*this);
 }
 
 bool prepare_pipe(int dev) {
+    const unsigned gen = g_generation.load();
+    if (g_pipe.device >= 0 && g_pipe.generation != gen) release_pipe(g_pipe, false);
     if (g_pipe.device != dev) {
         if (g_pipe.device >= 0) {
             cudaSetDevice(g_pipe.device);
@@ -156,22 +214,62 @@ bool prepare_pipe(int dev) {
             cudaSetDevice(dev);
         }
         g_pipe.device = dev;
+        g_pipe.generation = gen;
     }
     for (Slot& s : g_pipe.slot)
         if (!s.stream && fail(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    if (!g_pipe.idx_ready && fail(cudaEventCreateWithFlags(&g_pipe.idx_ready, cudaEventDisableTiming), "cudaEventCreate"))
+        return false;
     return true;
+}
+
+// Release staging buffers that an oversized call left behind (F = 9216 batches): they would otherwise stay
+// allocated until the calling thread exits.
+void trim_pipe() {
+    for (Slot& s : g_pipe.slot) {
+        auto trim = [](void** p, size_t* cap) {
+            if (*cap > kTrimBytes) {
+                cudaFree(*p);
+                *p = nullptr;
+                *cap = 0;
+            }
+        };
+        trim(&s.d_in, &s.in_cap);
+        trim(&s.d_out, &s.out_cap);
+        trim(&s.d_aux, &s.aux_cap);
+        trim(&s.d_scratch, &s.scratch_cap);
+    }
+}
+
+// Wait for a stream with a short spin on cudaStreamQuery before blocking: the drop-in call lasts tens of
+// microseconds, about what a blocking synchronise adds on its own.
+bool wait_stream(cudaStream_t stream, const char* what) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(stream);
+        if (e == cudaSuccess) return true;
+        if (e != cudaErrorNotReady) return !fail(e, what);
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) break;
+    }
+    return !fail(cudaStreamSynchronize(stream), what);
 }
 
 // Host-path chunk size in frames per pipeline stage.  The throughput kernel takes a flat ~0.38 us x (F+6)
 // for anything up to ~37,000 frames, the H2D copy of n frames takes n x 4(F+6) B / 55 GB/s, so the
-// kernel hides behind the copy once a chunk holds more than ~5,300 frames whatever F is; 12,288
-// leaves a 2x margin (profiles/e2e_chunk_sweep.py).  VITERBI_B200_CHUNK_FRAMES overrides it.
-size_t host_chunk_frames() {
-    static const size_t frames = [] {
+// kernel hides behind the copy once a chunk holds more than ~5,300 frames whatever F is; 12,288 leaves a 2x margin
+// at the FIC size (profiles/e2e_chunk_sweep.py).  Larger frames get proportionally fewer frames per chunk (about
+// 38 MB of symbols, never below 2,048 frames) so that the staging buffers and the decision scratch of a slot stay
+// bounded at F = 9216.  VITERBI_B200_CHUNK_FRAMES overrides it.
+size_t host_chunk_frames(unsigned framebits) {
+    static const long forced = [] {
         const char* env = getenv("VITERBI_B200_CHUNK_FRAMES");
-        const long v = (env && *env) ? atol(env) : 12288;
-        return (size_t)(v >= 64 ? v : 12288) & ~(size_t)63;
+        return (env && *env) ? atol(env) : 0L;
     }();
+    if (forced >= 64) return (size_t)forced & ~(size_t)63;
+    const size_t row = 4 * ((size_t)framebits + 6);
+    size_t frames = ((size_t)12288 * 3096 / row) & ~(size_t)63;
+    if (frames > 12288) frames = 12288;
+    if (frames < 2048) frames = 2048;
     return frames;
 }
 
@@ -197,7 +295,7 @@ int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_
         return fail(launch_viterbi_warp(d_syms, d_out, n, framebits, st->num_sms, stream), "viterbi warp kernel launch")
                    ? FEC_ERR_DEVICE
                    : FEC_OK;
-    const int blocks = viterbi_grid_blocks(st->num_sms, n);
+    const int blocks = viterbi_grid_blocks(st->num_sms, n, framebits);
     const size_t need = viterbi_scratch_bytes(blocks, framebits);
     void* ws = scratch;
     const bool own = (ws == nullptr) || scratch_cap < need;
@@ -217,6 +315,52 @@ bool puncture_index(unsigned framebits, const uint8_t* keep, size_t rx_per_frame
     int32_t next = 0;
     for (size_t p = 0; p < nsym; p++) idx[p] = keep[p] ? next++ : -1;
     return (size_t)next == rx_per_frame;
+}
+
+// The single-frame drop-in decode on this thread's bounce buffer: one graph launch + one wait.
+int dropin_launch(DeviceState* st, unsigned framebits, bool is_u32, const void* in, uint8_t* out, size_t n) {
+    Slot& s0 = g_pipe.slot[0];
+    DropinGraph* hit = nullptr;
+    DropinGraph* victim = &g_pipe.graph[0];
+    if (n == 1) {
+        for (DropinGraph& g : g_pipe.graph) {
+            if (g.exec && g.framebits == framebits && g.u32 == is_u32 && g.in == in && g.out == out) hit = &g;
+            if (g.last_use < victim->last_use) victim = &g;
+        }
+    }
+    if (hit) {
+        hit->last_use = ++g_pipe.graph_clock;
+        count_launch();
+        if (fail(cudaGraphLaunch(hit->exec, s0.stream), "cudaGraphLaunch")) return FEC_ERR_DEVICE;
+        return wait_stream(s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
+    }
+    auto launch = [&]() {
+        return is_u32 ? launch_viterbi_warp_u32((const uint32_t*)in, out, n, framebits, st->num_sms, s0.stream)
+                      : launch_viterbi_warp((const uint8_t*)in, out, n, framebits, st->num_sms, s0.stream);
+    };
+    if (n == 1) {
+        // first call of this shape: capture the launch into a graph and keep the executable
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool ok = cudaStreamBeginCapture(s0.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const cudaError_t le = launch();
+            const cudaError_t ce = cudaStreamEndCapture(s0.stream, &graph);
+            ok = le == cudaSuccess && ce == cudaSuccess && graph != nullptr &&
+                 cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        (void)cudaGetLastError();
+        if (ok) {
+            if (victim->exec) cudaGraphExecDestroy(victim->exec);
+            *victim = DropinGraph{exec, framebits, is_u32, in, out, ++g_pipe.graph_clock};
+            if (fail(cudaGraphLaunch(exec, s0.stream), "cudaGraphLaunch")) return FEC_ERR_DEVICE;
+            return wait_stream(s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
+        }
+        // capture not possible (e.g. the host application is capturing globally): plain launch below
+    }
+    if (fail(launch(), "viterbi warp kernel launch")) return FEC_ERR_DEVICE;
+    return wait_stream(s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
 }
 
 // Host-pointer batch: chunks pipelined over kPipe streams (H2D | kernel | D2H overlap).
@@ -239,9 +383,17 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
 
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
     const size_t in_row = punct ? rx_per_frame : nsym * (is_u32 ? 4 : 1);
-    if (punct && (!grow(&g_pipe.d_idx, &g_pipe.idx_cap, nsym * sizeof(int32_t)) ||
-                  fail(cudaMemcpy(g_pipe.d_idx, idx.data(), nsym * sizeof(int32_t), cudaMemcpyHostToDevice), "H2D index table")))
-        return FEC_ERR_DEVICE;
+    if (punct) {
+        // the table goes up on slot 0's stream; the other slots wait for the event (idx outlives the call's final
+        // synchronise, so the pageable source is safe)
+        if (!grow(&g_pipe.d_idx, &g_pipe.idx_cap, nsym * sizeof(int32_t)) ||
+            fail(cudaMemcpyAsync(g_pipe.d_idx, idx.data(), nsym * sizeof(int32_t), cudaMemcpyHostToDevice, g_pipe.slot[0].stream),
+                 "H2D index table") ||
+            fail(cudaEventRecord(g_pipe.idx_ready, g_pipe.slot[0].stream), "cudaEventRecord"))
+            return FEC_ERR_DEVICE;
+        for (int k = 1; k < kPipe; k++)
+            if (fail(cudaStreamWaitEvent(g_pipe.slot[k].stream, g_pipe.idx_ready, 0), "cudaStreamWaitEvent")) return FEC_ERR_DEVICE;
+    }
     // Small calls (the single-frame drop-in above all) bounce through this thread's pinned buffer: the driver's
     // pageable-copy path serialises concurrent callers (4 threads at F=3072 were slower than 1), a 50 KB memcpy
     // into pinned memory does not.
@@ -251,6 +403,7 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
     if (in_bytes + out_bytes <= kBounceBytes) {
         Slot& s0 = g_pipe.slot[0];
         const size_t in_pad = (in_bytes + 255) & ~(size_t)255;
+        if (s0.pin_cap < in_pad + out_bytes) drop_graphs(g_pipe, true);  // the graphs point into the old buffer
         if (!grow(&s0.h_pin, &s0.pin_cap, in_pad + out_bytes, true)) return FEC_ERR_DEVICE;
         memcpy(s0.h_pin, syms, in_bytes);
         syms = s0.h_pin;
@@ -260,20 +413,15 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
     // ... and when the warp-per-frame kernel would decode them anyway, it runs directly on the bounce buffer:
     // pinned memory is mapped into the device's address space, the kernel stages the symbols into shared memory
     // itself (compacting the u32 layout on the way) and writes the decoded bytes back through the mapping, so
-    // the call is one kernel launch and one synchronise -- no copy operations, no compaction kernel.
+    // the call is one (graph) launch and one wait -- no copy operations, no compaction kernel.
     if (bounce_out && !punct && n < kVitWarpKernelMaxFrames && g_vit_kernel.load() != FEC_VITERBI_PAIR) {
-        Slot& s0 = g_pipe.slot[0];
-        const cudaError_t e =
-            is_u32 ? launch_viterbi_warp_u32((const uint32_t*)syms, bounce_out, n, framebits, st->num_sms, s0.stream)
-                   : launch_viterbi_warp((const uint8_t*)syms, bounce_out, n, framebits, st->num_sms, s0.stream);
-        if (fail(e, "viterbi warp kernel launch") || fail(cudaStreamSynchronize(s0.stream), "cudaStreamSynchronize"))
-            return FEC_ERR_DEVICE;
-        memcpy(user_out, bounce_out, out_bytes);
-        return FEC_OK;
+        const int rc = dropin_launch(st, framebits, is_u32, syms, bounce_out, n);
+        if (rc == FEC_OK) memcpy(user_out, bounce_out, out_bytes);
+        return rc;
     }
     // chunks are pipelined over kPipe streams: the H2D copy of chunk k+1, the kernel of chunk k and the
     // D2H copy of chunk k-1 overlap
-    size_t chunk = host_chunk_frames();
+    size_t chunk = host_chunk_frames(framebits);
     if (chunk > n) chunk = n;
     int rc = FEC_OK;
     size_t done = 0;
@@ -282,7 +430,7 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
         const size_t m = (n - done < chunk) ? n - done : chunk;
         // the slot's previous chunk must have left its buffers
         if (fail(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize")) { rc = FEC_ERR_DEVICE; break; }
-        const int blocks = viterbi_grid_blocks(st->num_sms, m);
+        const int blocks = viterbi_grid_blocks(st->num_sms, m, framebits);
         if (!grow(&s.d_in, &s.in_cap, m * nsym) || !grow(&s.d_out, &s.out_cap, m * nout) ||
             !grow(&s.d_scratch, &s.scratch_cap, viterbi_scratch_bytes(blocks, framebits)) ||
             ((is_u32 || punct) && !grow(&s.d_aux, &s.aux_cap, m * in_row + 16))) {
@@ -323,11 +471,23 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
     for (Slot& s : g_pipe.slot)
         if (s.stream && fail(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
     if (bounce_out && rc == FEC_OK) memcpy(user_out, bounce_out, out_bytes);
+    trim_pipe();
     return rc;
 }
 
+// Device pointer through which a kernel can read the caller's host buffer directly, or nullptr when the buffer is
+// ordinary pageable memory (pinned memory -- fec_host_alloc(), cudaMallocHost, cudaHostRegister -- is mapped).
+const uint8_t* mapped_host_pointer(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return attr.type == cudaMemoryTypeHost ? (const uint8_t*)attr.devicePointer : nullptr;
+}
+
 int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret) {
-    if (s == 0 || s > 1024) return bad_arg("RSDims must be 1..1024");
+    if (s == 0 || s > kRsMaxDims) return bad_arg("RSDims must be 1..1024");
     if (n == 0) return FEC_OK;
     if (!in || !out || !ret) return bad_arg("null pointer");
     int dev;
@@ -335,22 +495,33 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
     if (!st) return FEC_ERR_DEVICE;
     if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
     const size_t in_row = 120 * (size_t)s, out_row = 110 * (size_t)s;
-    // small calls (the single-superframe drop-in): bounce through this thread's pinned buffer, see vit_host
-    uint8_t* bounce = nullptr;
-    uint8_t* const user_out = out;
-    int32_t* const user_ret = ret;
     const size_t in_bytes = n * in_row, out_bytes = n * out_row, ret_bytes = n * sizeof(int32_t);
     const size_t in_pad = (in_bytes + 255) & ~(size_t)255, out_pad = (out_bytes + 255) & ~(size_t)255;
     if (in_bytes + out_bytes <= kBounceBytes) {
+        // Small calls (the single-superframe drop-in): the kernel runs directly on this thread's pinned bounce
+        // buffer through its device mapping -- it stages the superframe from there, applies the partial-write rule
+        // to the copy of the caller's outVector in place and writes the return values next to it.  One kernel
+        // launch, one wait, no copy operations.  p == outVector (legal in the reference, which copies each column
+        // to rsBlock first: rschecksf.cpp:75-84) is safe: the input is copied before the output is touched.
         Slot& s0 = g_pipe.slot[0];
+        if (s0.pin_cap < in_pad + out_pad + ret_bytes) drop_graphs(g_pipe, true);
         if (!grow(&s0.h_pin, &s0.pin_cap, in_pad + out_pad + ret_bytes, true)) return FEC_ERR_DEVICE;
-        bounce = (uint8_t*)s0.h_pin;
+        uint8_t* bounce = (uint8_t*)s0.h_pin;
         memcpy(bounce, in, in_bytes);
         memcpy(bounce + in_pad, out, out_bytes);  // the partial-write rule keeps the caller's bytes
-        in = bounce;
-        out = bounce + in_pad;
-        ret = reinterpret_cast<int32_t*>(bounce + in_pad + out_pad);
+        int32_t* b_ret = reinterpret_cast<int32_t*>(bounce + in_pad + out_pad);
+        if (fail(launch_rs_superframes(bounce, bounce + in_pad, b_ret, nullptr, n, s, st->num_sms, s0.stream), "rs kernel launch") ||
+            !wait_stream(s0.stream, "rs superframe check"))
+            return FEC_ERR_DEVICE;
+        memcpy(out, bounce + in_pad, out_bytes);
+        memcpy(ret, b_ret, ret_bytes);
+        return FEC_OK;
     }
+    // The partial-write rule (rschecksf.cpp:80-88) leaves the columns from the first failing one on untouched, so
+    // the result rows are a merge of decoded bytes and the caller's current outVector bytes.  When outVector is
+    // pinned the kernel fetches the caller's bytes of FAILING superframes itself through the buffer's device
+    // mapping and produces complete rows, which are copied back whole; otherwise outVector is uploaded first.
+    const uint8_t* d_orig_base = mapped_host_pointer(out);
     size_t chunk = rs_chunk_bytes() / in_row;
     if (chunk < 1) chunk = 1;
     if (chunk > n) chunk = n;
@@ -365,11 +536,11 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
             rc = FEC_ERR_DEVICE;
             break;
         }
-        // the partial-write rule needs the caller's current output bytes on the device
+        const uint8_t* d_orig = d_orig_base ? d_orig_base + done * out_row : nullptr;
         if (fail(cudaMemcpyAsync(sl.d_in, in + done * in_row, m * in_row, cudaMemcpyHostToDevice, sl.stream), "H2D") ||
-            fail(cudaMemcpyAsync(sl.d_out, out + done * out_row, m * out_row, cudaMemcpyHostToDevice, sl.stream), "H2D out") ||
-            fail(launch_rs_superframes((const uint8_t*)sl.d_in, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux, m, s, st->num_sms,
-                                       sl.stream),
+            (!d_orig && fail(cudaMemcpyAsync(sl.d_out, out + done * out_row, m * out_row, cudaMemcpyHostToDevice, sl.stream), "H2D out")) ||
+            fail(launch_rs_superframes((const uint8_t*)sl.d_in, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux, d_orig, m, s,
+                                       st->num_sms, sl.stream),
                  "rs kernel launch") ||
             fail(cudaMemcpyAsync(out + done * out_row, sl.d_out, m * out_row, cudaMemcpyDeviceToHost, sl.stream), "D2H") ||
             fail(cudaMemcpyAsync(ret + done, sl.d_aux, m * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ret")) {
@@ -380,11 +551,171 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
     }
     for (Slot& sl : g_pipe.slot)
         if (sl.stream && fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
-    if (bounce && rc == FEC_OK) {
-        memcpy(user_out, out, out_bytes);
-        memcpy(user_ret, ret, ret_bytes);
+    trim_pipe();
+    return rc;
+}
+
+// Viterbi -> superframe -> RS with host buffers, one device (the calling thread's).
+int dabplus_host(unsigned framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret);
+
+// ---- multi-device host calls --------------------------------------------------------------------------------
+// Frames and superframes are independent (deconvolve.cpp:116-132 re-initialises the metrics per call,
+// rschecksf.cpp:72 uses stack scratch), so one host batch is cut into contiguous shards, one per selected
+// device, and each shard runs the single-device host path on its own worker thread (own streams, own staging
+// buffers) -- no exchange between devices.  Workers are persistent so that their staging state survives calls.
+struct Worker {
+    int dev = -1;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = false, quit = false;
+    int rc = FEC_OK;
+    std::string error;
+
+    void loop() {
+        t_device = dev;
+        std::unique_lock<std::mutex> lock(mu);
+        for (;;) {
+            cv.wait(lock, [this] { return has_job || quit; });
+            if (quit) return;
+            lock.unlock();
+            t_error.clear();
+            const int r = job();
+            lock.lock();
+            rc = r;
+            error = t_error;
+            has_job = false;
+            done = true;
+            cv.notify_all();
+        }
+    }
+};
+
+struct WorkerPool {
+    std::mutex mu;  // serialises multi-device calls (each already uses every selected device)
+    std::vector<int> devices;  // empty = all visible devices
+    std::unique_ptr<Worker> worker[kMaxDevices];
+
+    ~WorkerPool() {
+        for (auto& w : worker) {
+            if (!w) continue;
+            {
+                std::lock_guard<std::mutex> lock(w->mu);
+                w->quit = true;
+            }
+            w->cv.notify_all();
+            if (w->th.joinable()) w->th.join();
+        }
+    }
+
+    Worker* get(int dev) {
+        if (!worker[dev]) {
+            worker[dev].reset(new Worker());
+            worker[dev]->dev = dev;
+            worker[dev]->th = std::thread([w = worker[dev].get()] { w->loop(); });
+        }
+        return worker[dev].get();
+    }
+};
+WorkerPool g_pool;
+
+// devices of the multi-device calls (pool mutex held)
+bool selected_devices(std::vector<int>& devs) {
+    devs = g_pool.devices;
+    if (devs.empty()) {
+        int n = 0;
+        if (fail(cudaGetDeviceCount(&n), "cudaGetDeviceCount") || n < 1) {
+            if (t_error.empty()) t_error = "no CUDA device";
+            return false;
+        }
+        for (int i = 0; i < n && i < kMaxDevices; i++) devs.push_back(i);
+    }
+    return true;
+}
+
+// Cut `units` work units into one contiguous range per device (boundaries on multiples of `align` units) and run
+// fn(lo, hi) for each non-empty range on that device's worker.  Returns the first failure.
+int run_sharded(size_t units, size_t align, const std::function<int(size_t, size_t)>& fn) {
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    std::vector<int> devs;
+    if (!selected_devices(devs)) return FEC_ERR_DEVICE;
+    const size_t world = devs.size(), blocks = (units + align - 1) / align;
+    std::vector<Worker*> used;
+    for (size_t r = 0; r < world; r++) {
+        size_t lo = blocks * r / world * align, hi = blocks * (r + 1) / world * align;
+        if (lo > units) lo = units;
+        if (hi > units) hi = units;
+        if (lo == hi) continue;
+        Worker* w = g_pool.get(devs[r]);
+        {
+            std::lock_guard<std::mutex> wl(w->mu);
+            w->job = [&fn, lo, hi] { return fn(lo, hi); };
+            w->has_job = true;
+            w->done = false;
+        }
+        w->cv.notify_all();
+        used.push_back(w);
+    }
+    int rc = FEC_OK;
+    for (Worker* w : used) {
+        std::unique_lock<std::mutex> wl(w->mu);
+        w->cv.wait(wl, [w] { return w->done; });
+        if (w->rc != FEC_OK && rc == FEC_OK) {
+            rc = w->rc;
+            t_error = "device " + std::to_string(w->dev) + ": " + w->error;
+        }
     }
     return rc;
+}
+
+// ---- NCCL, loaded at run time (the library has no link-time dependency on it): the one collective of the design,
+// the gather of result arrays over NVLink, for hosts that keep the shards on the devices.
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::vector<int> devs;
+    std::vector<ncclComm_t> comms;
+};
+NcclApi g_nccl;
+
+bool nccl_load() {
+    if (g_nccl.handle) return true;
+    const char* env = getenv("VITERBI_B200_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names)
+        if (nm && *nm && (h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!h) {
+        t_error = "NCCL not found (libnccl.so.2; set VITERBI_B200_NCCL_LIB)";
+        return false;
+    }
+    auto sym = [h](const char* n) { return dlsym(h, n); };
+    g_nccl.CommInitAll = (int (*)(ncclComm_t*, int, const int*))sym("ncclCommInitAll");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))sym("ncclCommDestroy");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))sym("ncclAllGather");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.AllGather) {
+        t_error = "NCCL library lacks a required symbol";
+        dlclose(h);
+        return false;
+    }
+    g_nccl.handle = h;
+    return true;
+}
+
+bool nccl_fail(int r, const char* what) {
+    if (r == 0) return false;
+    t_error = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error");
+    return true;
 }
 
 // ---- optional call log (the run-time counterpart of the reference's VIT_WRITE_LOGFILE build,
@@ -464,6 +795,64 @@ class CallLog {
 
 }  // namespace
 
+namespace {
+
+int dabplus_host(unsigned framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret) {
+    if (!vit_args_ok(framebits) || framebits == 0 || framebits % 192u) return bad_arg("framebits must be a multiple of 192");
+    if (nsf == 0) return FEC_OK;
+    if (!syms || !out || !ret) return bad_arg("null pointer");
+    int dev;
+    DeviceState* st = device_state(&dev);
+    if (!st) return FEC_ERR_DEVICE;
+    if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
+    const unsigned rsdims = framebits / 192u;
+    const size_t nsym = 4 * ((size_t)framebits + 6), in_row = 5 * nsym, out_row = 110 * (size_t)rsdims;
+    const uint8_t* d_orig_base = mapped_host_pointer(out);  // see rs_host: no upload of a pinned `out`
+    size_t chunk = host_chunk_frames(framebits) / 5;
+    if (chunk < 1) chunk = 1;
+    if (chunk > nsf) chunk = nsf;
+    int rc = FEC_OK;
+    size_t done = 0;
+    for (int k = 0; done < nsf && rc == FEC_OK; k++) {
+        Slot& sl = g_pipe.slot[k % kPipe];
+        const size_t m = (nsf - done < chunk) ? nsf - done : chunk;
+        if (fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize")) { rc = FEC_ERR_DEVICE; break; }
+        const int blocks = viterbi_grid_blocks(st->num_sms, m * 5, framebits);
+        // d_scratch: [decoded frames = superframes, 120*s bytes each][Viterbi decision scratch]
+        const size_t bits_bytes = (m * 120 * (size_t)rsdims + 255) & ~(size_t)255;
+        const size_t scratch_bytes = viterbi_scratch_bytes(blocks, framebits);
+        if (!grow(&sl.d_in, &sl.in_cap, m * in_row) || !grow(&sl.d_out, &sl.out_cap, m * out_row) ||
+            !grow(&sl.d_aux, &sl.aux_cap, m * sizeof(int32_t)) || !grow(&sl.d_scratch, &sl.scratch_cap, bits_bytes + scratch_bytes)) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        uint8_t* d_bits = (uint8_t*)sl.d_scratch;
+        const uint8_t* d_orig = d_orig_base ? d_orig_base + done * out_row : nullptr;
+        if (fail(cudaMemcpyAsync(sl.d_in, syms + done * in_row, m * in_row, cudaMemcpyHostToDevice, sl.stream), "H2D") ||
+            (!d_orig && fail(cudaMemcpyAsync(sl.d_out, out + done * out_row, m * out_row, cudaMemcpyHostToDevice, sl.stream), "H2D out"))) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        rc = vit_device(st, framebits, (const uint8_t*)sl.d_in, m * 5, d_bits, sl.stream, d_bits + bits_bytes,
+                        sl.scratch_cap - bits_bytes);
+        if (rc != FEC_OK) break;
+        if (fail(launch_rs_superframes(d_bits, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux, d_orig, m, rsdims, st->num_sms, sl.stream),
+                 "rs kernel launch") ||
+            fail(cudaMemcpyAsync(out + done * out_row, sl.d_out, m * out_row, cudaMemcpyDeviceToHost, sl.stream), "D2H") ||
+            fail(cudaMemcpyAsync(ret + done, sl.d_aux, m * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ret")) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
+        done += m;
+    }
+    for (Slot& sl : g_pipe.slot)
+        if (sl.stream && fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
+    trim_pipe();
+    return rc;
+}
+
+}  // namespace
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 }  // namespace fec
@@ -515,6 +904,27 @@ int initialize(void) {
     configure_call_log();  // the reference re-reads its configuration here (dllmain.cpp:158 -> SetupDLL)
     const char* env = getenv("VITERBI_B200_DEVICE");
     if (env && *env) g_device.store(atoi(env));
+    DeviceState* st = device_state();
+    // The reference's initialize() is how a host recovers after a fault (exc_handler.cpp:214 -> dllmain.cpp:156):
+    // probe the context, and after a sticky CUDA error tear it down, declare all staging state of the old context
+    // dead (threads drop theirs on their next call) and set the device up again.
+    if (st && cudaDeviceSynchronize() == cudaSuccess) return 1;
+    (void)cudaGetLastError();
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur < 0 || cur >= kMaxDevices) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    if (cudaDeviceReset() != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    g_generation.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lock(g_dev[cur].mu);
+        g_dev[cur].ready = false;
+    }
+    t_error.clear();
     return device_state() != nullptr;
 }
 
@@ -555,7 +965,7 @@ int viterbi_deconvolve_batch_u32_device(unsigned int framebits, const uint32_t* 
     if (!vit_args_ok(framebits)) return bad_arg("framebits must be even and <= 9216");
     if (n == 0 || framebits == 0) return FEC_OK;
     if (!d_syms || !d_out) return bad_arg("null pointer");
-    if (reinterpret_cast<uintptr_t>(d_syms) & 15) return bad_arg("d_syms must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_syms) & 15) return bad_arg("d_syms must be 16-byte aligned (one trellis step per uint4)");
     DeviceState* st = device_state();
     if (!st) return FEC_ERR_DEVICE;
     cudaStream_t s = (cudaStream_t)stream;
@@ -618,12 +1028,12 @@ int rs_check_superframe_batch(const uint8_t* in, unsigned int RSDims, size_t n, 
 
 int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
                                      int32_t* d_ret, void* stream) {
-    if (RSDims == 0 || RSDims > 1024) return bad_arg("RSDims must be 1..1024");
+    if (RSDims == 0 || RSDims > kRsMaxDims) return bad_arg("RSDims must be 1..1024");
     if (n == 0) return FEC_OK;
     if (!d_in || !d_out || !d_ret) return bad_arg("null pointer");
     DeviceState* st = device_state();
     if (!st) return FEC_ERR_DEVICE;
-    return fail(launch_rs_superframes(d_in, d_out, d_ret, n, RSDims, st->num_sms, (cudaStream_t)stream), "rs kernel launch")
+    return fail(launch_rs_superframes(d_in, d_out, d_ret, nullptr, n, RSDims, st->num_sms, (cudaStream_t)stream), "rs kernel launch")
                ? FEC_ERR_DEVICE
                : FEC_OK;
 }
@@ -643,7 +1053,7 @@ int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_s
     void* d_bits = nullptr;
     if (fail(cudaMallocAsync(&d_bits, nsf * 120 * (size_t)rsdims, s), "cudaMallocAsync(decoded frames)")) return FEC_ERR_DEVICE;
     int rc = vit_device(st, framebits, d_syms, nsf * 5, (uint8_t*)d_bits, s, nullptr, 0);
-    if (rc == FEC_OK && fail(launch_rs_superframes((const uint8_t*)d_bits, d_out, d_ret, nsf, rsdims, st->num_sms, s),
+    if (rc == FEC_OK && fail(launch_rs_superframes((const uint8_t*)d_bits, d_out, d_ret, nullptr, nsf, rsdims, st->num_sms, s),
                              "rs kernel launch"))
         rc = FEC_ERR_DEVICE;
     (void)cudaFreeAsync(d_bits, s);
@@ -651,46 +1061,143 @@ int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_s
 }
 
 int dabplus_decode_superframes(unsigned int framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret) {
-    if (!vit_args_ok(framebits) || framebits == 0 || framebits % 192u) return bad_arg("framebits must be a multiple of 192");
-    if (nsf == 0) return FEC_OK;
-    if (!syms || !out || !ret) return bad_arg("null pointer");
-    int dev;
-    DeviceState* st = device_state(&dev);
-    if (!st) return FEC_ERR_DEVICE;
-    if (!prepare_pipe(dev)) return FEC_ERR_DEVICE;
-    const unsigned rsdims = framebits / 192u;
-    const size_t nsym = 4 * ((size_t)framebits + 6), in_row = 5 * nsym, out_row = 110 * (size_t)rsdims;
-    size_t chunk = host_chunk_frames() / 5;
-    if (chunk < 1) chunk = 1;
-    if (chunk > nsf) chunk = nsf;
-    int rc = FEC_OK;
-    size_t done = 0;
-    for (int k = 0; done < nsf && rc == FEC_OK; k++) {
-        Slot& sl = g_pipe.slot[k % kPipe];
-        const size_t m = (nsf - done < chunk) ? nsf - done : chunk;
-        if (fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize")) { rc = FEC_ERR_DEVICE; break; }
-        if (!grow(&sl.d_in, &sl.in_cap, m * in_row) || !grow(&sl.d_out, &sl.out_cap, m * out_row) ||
-            !grow(&sl.d_aux, &sl.aux_cap, m * sizeof(int32_t))) {
-            rc = FEC_ERR_DEVICE;
-            break;
-        }
-        if (fail(cudaMemcpyAsync(sl.d_in, syms + done * in_row, m * in_row, cudaMemcpyHostToDevice, sl.stream), "H2D") ||
-            fail(cudaMemcpyAsync(sl.d_out, out + done * out_row, m * out_row, cudaMemcpyHostToDevice, sl.stream), "H2D out")) {
-            rc = FEC_ERR_DEVICE;
-            break;
-        }
-        rc = dabplus_decode_superframes_device(framebits, (const uint8_t*)sl.d_in, m, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux,
-                                               sl.stream);
-        if (rc != FEC_OK) break;
-        if (fail(cudaMemcpyAsync(out + done * out_row, sl.d_out, m * out_row, cudaMemcpyDeviceToHost, sl.stream), "D2H") ||
-            fail(cudaMemcpyAsync(ret + done, sl.d_aux, m * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ret")) {
-            rc = FEC_ERR_DEVICE;
-            break;
-        }
-        done += m;
+    CallLog log("dabplus", framebits, nsf, syms, out);
+    const int rc = dabplus_host(framebits, syms, nsf, out, ret);
+    log.result(rc);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-device host calls: one batch, all selected devices, one process
+// ---------------------------------------------------------------------------------------------
+int viterbi_deconvolve_batch_multi(unsigned int framebits, const uint8_t* syms, size_t n, uint8_t* out) {
+    CallLog log("deco_multi", framebits, n, syms, out);
+    int rc;
+    if (!vit_args_ok(framebits))
+        rc = bad_arg("framebits must be even and <= 9216");
+    else if (n == 0 || framebits == 0)
+        rc = FEC_OK;
+    else if (!syms || !out)
+        rc = bad_arg("null pointer");
+    else {
+        const size_t row = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
+        rc = run_sharded(n, 64, [=](size_t lo, size_t hi) {  // 64 frames = one warp group of the kernel
+            return vit_host(framebits, syms + lo * row, SymFormat::U8, hi - lo, out + lo * nout);
+        });
     }
-    for (Slot& sl : g_pipe.slot)
-        if (sl.stream && fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
+    log.result(rc);
+    return rc;
+}
+
+int rs_check_superframe_batch_multi(const uint8_t* in, unsigned int RSDims, size_t n, uint8_t* out, int32_t* ret) {
+    CallLog log("rssf_multi", RSDims, n, in, out);
+    int rc;
+    if (RSDims == 0 || RSDims > kRsMaxDims)
+        rc = bad_arg("RSDims must be 1..1024");
+    else if (n == 0)
+        rc = FEC_OK;
+    else if (!in || !out || !ret)
+        rc = bad_arg("null pointer");
+    else
+        rc = run_sharded(n, 1, [=](size_t lo, size_t hi) {
+            return rs_host(in + lo * 120 * (size_t)RSDims, RSDims, hi - lo, out + lo * 110 * (size_t)RSDims, ret + lo);
+        });
+    log.result(rc);
+    return rc;
+}
+
+int dabplus_decode_superframes_multi(unsigned int framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret) {
+    CallLog log("dabplus_multi", framebits, nsf, syms, out);
+    int rc;
+    if (!vit_args_ok(framebits) || framebits == 0 || framebits % 192u)
+        rc = bad_arg("framebits must be a multiple of 192");
+    else if (nsf == 0)
+        rc = FEC_OK;
+    else if (!syms || !out || !ret)
+        rc = bad_arg("null pointer");
+    else {
+        const size_t in_row = 5 * 4 * ((size_t)framebits + 6), out_row = 110 * (size_t)(framebits / 192u);
+        rc = run_sharded(nsf, 1, [=](size_t lo, size_t hi) {  // whole superframes: the 5 frames of one stay together
+            return dabplus_host(framebits, syms + lo * in_row, hi - lo, out + lo * out_row, ret + lo);
+        });
+    }
+    log.result(rc);
+    return rc;
+}
+
+int fec_set_devices(const int* ordinals, int count) {
+    if (count < 0 || count > kMaxDevices || (count > 0 && !ordinals)) return bad_arg("bad device list");
+    int ndev = 0;
+    if (fail(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return FEC_ERR_DEVICE;
+    std::vector<int> devs;
+    for (int i = 0; i < count; i++) {
+        if (ordinals[i] < 0 || ordinals[i] >= ndev || ordinals[i] >= kMaxDevices) return bad_arg("device ordinal out of range");
+        for (int d : devs)
+            if (d == ordinals[i]) return bad_arg("duplicate device ordinal");
+        devs.push_back(ordinals[i]);
+    }
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    if (devs != g_pool.devices && !g_nccl.comms.empty()) {  // communicators belong to the old device list
+        for (ncclComm_t c : g_nccl.comms) g_nccl.CommDestroy(c);
+        g_nccl.comms.clear();
+        g_nccl.devs.clear();
+    }
+    g_pool.devices = devs;
+    return FEC_OK;
+}
+
+int fec_get_devices(int* ordinals, int capacity) {
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    std::vector<int> devs;
+    if (!selected_devices(devs)) return 0;
+    for (int i = 0; i < (int)devs.size() && i < capacity; i++)
+        if (ordinals) ordinals[i] = devs[i];
+    return (int)devs.size();
+}
+
+int fec_set_thread_device(int ordinal) {
+    if (ordinal < -1 || ordinal >= kMaxDevices) return bad_arg("device ordinal out of range");
+    t_device = ordinal;
+    if (ordinal < 0) return FEC_OK;
+    return device_state() ? FEC_OK : FEC_ERR_DEVICE;
+}
+
+// ncclAllGather over the selected devices from this one process (communicators from ncclCommInitAll, created on
+// first use): shard i (bytes_per_shard bytes at d_shard[i], on device i of the list) ends up at offset
+// i * bytes_per_shard of every d_all[j].  Enqueued on streams[i] (NULL array or entries = default stream).
+int fec_allgather_device(const void* const* d_shard, void* const* d_all, size_t bytes_per_shard, void* const* streams) {
+    if (!d_shard || !d_all) return bad_arg("null pointer");
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    std::vector<int> devs;
+    if (!selected_devices(devs)) return FEC_ERR_DEVICE;
+    for (size_t i = 0; i < devs.size(); i++)
+        if (!d_shard[i] || !d_all[i]) return bad_arg("null pointer");
+    if (bytes_per_shard == 0) return FEC_OK;
+    if (!nccl_load()) return FEC_ERR_DEVICE;
+    int cur = -1;
+    (void)cudaGetDevice(&cur);
+    if (g_nccl.devs != devs) {
+        for (ncclComm_t c : g_nccl.comms) g_nccl.CommDestroy(c);
+        g_nccl.comms.assign(devs.size(), nullptr);
+        if (nccl_fail(g_nccl.CommInitAll(g_nccl.comms.data(), (int)devs.size(), devs.data()), "ncclCommInitAll")) {
+            g_nccl.comms.clear();
+            g_nccl.devs.clear();
+            return FEC_ERR_DEVICE;
+        }
+        g_nccl.devs = devs;
+    }
+    int rc = FEC_OK;
+    if (nccl_fail(g_nccl.GroupStart(), "ncclGroupStart")) return FEC_ERR_DEVICE;
+    for (size_t i = 0; i < devs.size() && rc == FEC_OK; i++) {
+        if (fail(cudaSetDevice(devs[i]), "cudaSetDevice") ||
+            nccl_fail(g_nccl.AllGather(d_shard[i], d_all[i], bytes_per_shard, /*ncclUint8*/ 1, g_nccl.comms[i],
+                                       streams ? (cudaStream_t)streams[i] : nullptr),
+                      "ncclAllGather"))
+            rc = FEC_ERR_DEVICE;
+    }
+    if (nccl_fail(g_nccl.GroupEnd(), "ncclGroupEnd")) rc = FEC_ERR_DEVICE;
+    count_launch();
+    if (cur >= 0) (void)cudaSetDevice(cur);
     return rc;
 }
 

@@ -23,11 +23,15 @@ constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision
 // between 4,096 and 8,192 frames at F=768, between 2,048 and 4,096 at F=3072.
 constexpr unsigned long long kVitWarpKernelMaxFrames = 4096;
 constexpr int kRsThreads = 128;
+constexpr uint32_t kMaxFramebits = 9216;  // decision array bound of the reference, deconvolve.cpp:127
+constexpr uint32_t kRsMaxDims = 1024;     // one superframe must fit a shared-memory tile (120 KB)
 
 void count_launch();
 
 size_t viterbi_scratch_bytes(int grid_blocks, uint32_t framebits);
-int viterbi_grid_blocks(int num_sms, unsigned long long nframes);
+int viterbi_grid_blocks(int num_sms, unsigned long long nframes, uint32_t framebits);
+size_t viterbi_warp_smem_bytes(uint32_t framebits);
+cudaError_t viterbi_configure_device();
 cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_scratch, unsigned long long nframes,
                                 uint32_t framebits, int grid_blocks, cudaStream_t stream);
 cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
@@ -42,7 +46,10 @@ cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t 
 size_t rs_smem_bytes(uint32_t s, uint32_t sf_per_block);
 uint32_t rs_superframes_per_block(uint32_t s);
 cudaError_t rs_upload_tables();
-cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, unsigned long long nsf,
-                                  uint32_t s, int num_sms, cudaStream_t stream);
+cudaError_t rs_configure_device();
+// d_orig: nullptr = in-place semantics (d_out already holds the caller's bytes; untouched columns are not written);
+// else every byte of d_out is written, untouched columns copied from d_orig (same layout as d_out).
+cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, const uint8_t* d_orig,
+                                  unsigned long long nsf, uint32_t s, int num_sms, cudaStream_t stream);
 
 }  // namespace fec

@@ -73,7 +73,7 @@ struct DevicePolicy {
 #endif
 __global__ void __launch_bounds__(kRsThreads, RS_MIN_BLOCKS)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
-                     unsigned long long nsf, uint32_t s, uint32_t sf_per_block) {
+                     const uint8_t* __restrict__ orig, unsigned long long nsf, uint32_t s, uint32_t sf_per_block) {
     extern __shared__ __align__(16) uint8_t smem[];
     int* s_fail = reinterpret_cast<int*>(smem);
     int* s_sum = s_fail + sf_per_block;
@@ -143,10 +143,40 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                 for (size_t w = tid; w < nwords; w += blockDim.x)
                     reinterpret_cast<uint32_t*>(d + nhead)[w] = __byte_perm(tw[w], tw[w + 1], sel);
                 for (size_t i = nhead + nwords * 4 + tid; i < sf_out; i += blockDim.x) d[i] = t[i];
-            } else if (fail > 0) {
+            } else if (orig == nullptr) {
                 // i % s through a multiply-high (s is launch-uniform; exact for i < 2^17, s <= 1024)
-                for (uint32_t i = tid; i < (uint32_t)sf_out; i += blockDim.x)
-                    if (i - __umulhi(i, inv_s) * s < fail) d[i] = t[i];
+                if (fail > 0)
+                    for (uint32_t i = tid; i < (uint32_t)sf_out; i += blockDim.x)
+                        if (i - __umulhi(i, inv_s) * s < fail) d[i] = t[i];
+            } else {
+                // Host path without an upload of the caller's outVector: `out` is a staging buffer that is copied
+                // back whole, so every byte of the row is produced here -- decoded columns from the tile, the
+                // untouched ones (rschecksf.cpp:85-88) from the caller's own bytes, read through the device mapping
+                // of the caller's pinned buffer.  Only failing superframes read it: aligned 32-bit loads, so a warp
+                // asks for whole 128-byte lines across PCIe.
+                const uint8_t* o = orig + (sf0 + n) * sf_out;
+                const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3);
+                const uint32_t nhead = head < sf_out ? head : (uint32_t)sf_out;
+                auto col = [&](uint32_t i) { return i - __umulhi(i, inv_s) * s; };
+                if (tid < nhead) d[tid] = col(tid) < fail ? t[tid] : o[tid];
+                const uint32_t nwords = (uint32_t)((sf_out - nhead) / 4);
+                const uint32_t toff = (uint32_t)(reinterpret_cast<uintptr_t>(t + nhead) & 3);
+                const uint32_t* tw = reinterpret_cast<const uint32_t*>(t + nhead - toff);
+                const uint32_t tsel = 0x3210u + 0x1111u * toff;
+                const uint32_t ooff = (uint32_t)(reinterpret_cast<uintptr_t>(o + nhead) & 3);
+                const uint32_t* ow = reinterpret_cast<const uint32_t*>(o + nhead - ooff);
+                const uint32_t osel = 0x3210u + 0x1111u * ooff;
+                for (uint32_t w = tid; w < nwords; w += blockDim.x) {
+                    // the second word is only touched when it holds a byte of this row (never past the caller's array)
+                    const uint32_t o0 = ow[w], o1 = ooff ? ow[w + 1] : 0u;
+                    const uint32_t ov = __byte_perm(o0, o1, osel), tv = __byte_perm(tw[w], tw[w + 1], tsel);
+                    const uint32_t i0 = nhead + 4 * w;
+                    const uint32_t keep = (col(i0) < fail ? 0x000000FFu : 0u) | (col(i0 + 1) < fail ? 0x0000FF00u : 0u) |
+                                          (col(i0 + 2) < fail ? 0x00FF0000u : 0u) | (col(i0 + 3) < fail ? 0xFF000000u : 0u);
+                    reinterpret_cast<uint32_t*>(d + nhead)[w] = (tv & keep) | (ov & ~keep);
+                }
+                for (uint32_t i = nhead + nwords * 4 + tid; i < (uint32_t)sf_out; i += blockDim.x)
+                    d[i] = col(i) < fail ? t[i] : o[i];
             }
         }
     }
@@ -200,17 +230,17 @@ cudaError_t rs_upload_tables() {
     return cudaMemcpyToSymbol(c_tables, &h, sizeof(h));
 }
 
-cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, unsigned long long nsf,
-                                  uint32_t s, int num_sms, cudaStream_t stream) {
+// opt-in to the largest tile (one superframe of kRsMaxDims codewords) once per device, see viterbi_configure_device()
+cudaError_t rs_configure_device() {
+    return cudaFuncSetAttribute(rs_superframe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)rs_smem_bytes(kRsMaxDims, 1));
+}
+
+cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, const uint8_t* d_orig,
+                                  unsigned long long nsf, uint32_t s, int num_sms, cudaStream_t stream) {
     if (nsf == 0) return cudaSuccess;
     const uint32_t spb = rs_superframes_per_block(s);
     const size_t smem = rs_smem_bytes(s, spb);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(rs_superframe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
     unsigned long long nblk = (nsf + spb - 1) / spb;
     // persistent grid: exactly the blocks that are resident at once, so each block stages the tables once
     int per_sm = 0;
@@ -221,7 +251,7 @@ cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* 
     }
     const unsigned long long cap = (unsigned long long)num_sms * (unsigned)per_sm;
     if (nblk > cap) nblk = cap;
-    rs_superframe_kernel<<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, nsf, s, spb);
+    rs_superframe_kernel<<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, d_orig, nsf, s, spb);
     count_launch();
     return cudaGetLastError();
 }

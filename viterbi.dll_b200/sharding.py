@@ -37,5 +37,9 @@ def gather_to_all(local, n_total: int, world: int, rank: int, align: int = 1, gr
     padded[: hi - lo] = local
     out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
+    if out.is_cuda:
+        # The collective is complete on return, not merely enqueued: a rank that goes on to tear its communicator
+        # down while peers are still inside the all-gather leaves them in the NCCL watchdog (seen once at N = 8).
+        torch.cuda.current_stream(out.device).synchronize()
     parts = [out[r * width : r * width + (h - l)] for r, (l, h) in enumerate(bounds)]
     return torch.cat(parts, dim=0)
