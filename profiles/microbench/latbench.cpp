@@ -51,8 +51,19 @@ int main(int argc, char** argv) {
         const size_t nsym = 4 * (F + 6);
         const int nbuf = 16;  // distinct frames, not one cache-resident buffer
         std::vector<std::vector<unsigned>> sym(nbuf, std::vector<unsigned>(nsym));
-        for (auto& s : sym) {  // noisy symbols of a random codeword are not needed for timing: random bytes around the two levels
-            for (auto& w : s) w = (unsigned)((rnd() & 1 ? 172 : 83) + (int)(rnd() % 61) - 30);
+        for (auto& s : sym) {  // random bits -> K=7 rate-1/4 encoder -> AWGN at Eb/N0 = 3 dB -> u8 (viterbi-benchmark.cpp:304-311,658-670)
+            static const unsigned poly[4] = {109, 79, 83, 109};
+            const double amp = 1.0 / std::sqrt(0.5 / std::pow(10.0, (3.0 + 10.0 * std::log10(0.25)) / 10.0));
+            unsigned sr = 0;
+            for (unsigned t = 0; t < F + 6; t++) {
+                sr = (sr << 1) | (t < F ? (unsigned)(rnd() >> 63) : 0u);
+                for (int j = 0; j < 4; j++) {
+                    const double u1 = ((rnd() >> 11) + 1) * (1.0 / 9007199254740993.0), u2 = (rnd() >> 11) * (1.0 / 9007199254740992.0);
+                    const double g = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+                    const double v = 127.5 + 32.0 * ((__builtin_popcount(sr & poly[j]) & 1 ? amp : -amp) + g);
+                    s[4 * t + j] = (unsigned)(v < 0 ? 0 : v > 255 ? 255 : (int)v) | 0xABCD0000u;  // upper bytes are ignored (README.md:19)
+                }
+            }
         }
         std::vector<unsigned char> out(F / 8), want(F / 8);
         int bad = 0;

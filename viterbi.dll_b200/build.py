@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libviterbi_b200.so")
 # scheduler hoists the packed-min instructions far ahead of the predicated IMADs that consume their
 # predicate outputs, runs out of the 7 predicate registers and spills predicates through LOP3 pairs
 # (2642 vs 607 LOP3 in the loop body); -O1 keeps program order, which is already interleaved.
-SOURCES = {"viterbi_kernels.cu": ["-Xptxas", "-O1"], "rs_kernels.cu": [], "fec_api.cu": []}
+SOURCES = {"viterbi_kernels.cu": ["-Xptxas", "-O1"], "viterbi_warp_kernel.cu": [], "rs_kernels.cu": [], "fec_api.cu": []}
 HEADERS = [os.path.join(CSRC, "fec_internal.h"), os.path.join(CSRC, "rs_chien_bitsliced.h"), os.path.join(CSRC, "rs_decode.h"), os.path.join(CSRC, "viterbi_pair_core.h"),
            os.path.join(CSRC, "rs_bitslice_tables.h"), os.path.join(os.path.dirname(HERE), "include", "viterbi_b200.h")]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

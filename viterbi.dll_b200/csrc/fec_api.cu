@@ -66,9 +66,9 @@ struct Slot {
 struct DropinGraph {
     cudaGraphExec_t exec = nullptr;
     unsigned framebits = 0;
-    bool u32 = false;
     const void* in = nullptr;
     void* out = nullptr;
+    void* flag = nullptr;
     unsigned long long last_use = 0;
 };
 
@@ -317,27 +317,42 @@ bool puncture_index(unsigned framebits, const uint8_t* keep, size_t rx_per_frame
     return (size_t)next == rx_per_frame;
 }
 
-// The single-frame drop-in decode on this thread's bounce buffer: one graph launch + one wait.
-int dropin_launch(DeviceState* st, unsigned framebits, bool is_u32, const void* in, uint8_t* out, size_t n) {
+// Wait for the completion flag the warp kernel raises in the pinned bounce buffer (a PCIe write the host sees about a
+// microsecond after the kernel's last store -- several microseconds earlier than a stream synchronise returns).  The
+// stream is queried now and then so that a failed launch cannot leave the caller spinning.
+bool wait_flag(volatile uint32_t* flag, cudaStream_t stream, const char* what) {
+    for (unsigned spins = 1;; spins++) {
+        if (*flag != 0u) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return true;
+        }
+        if ((spins & 0x3FFu) == 0) {
+            const cudaError_t e = cudaStreamQuery(stream);
+            if (e == cudaSuccess) return true;  // kernel done: its stores, the flag included, are visible
+            if (e != cudaErrorNotReady) return !fail(e, what);
+        }
+    }
+}
+
+// The single-frame drop-in decode on this thread's bounce buffer: one graph launch + one wait on the flag.
+int dropin_launch(DeviceState* st, unsigned framebits, const uint8_t* in, uint8_t* out, uint32_t* flag, size_t n) {
     Slot& s0 = g_pipe.slot[0];
     DropinGraph* hit = nullptr;
     DropinGraph* victim = &g_pipe.graph[0];
     if (n == 1) {
         for (DropinGraph& g : g_pipe.graph) {
-            if (g.exec && g.framebits == framebits && g.u32 == is_u32 && g.in == in && g.out == out) hit = &g;
+            if (g.exec && g.framebits == framebits && g.in == in && g.out == out && g.flag == flag) hit = &g;
             if (g.last_use < victim->last_use) victim = &g;
         }
     }
+    *reinterpret_cast<volatile uint32_t*>(flag) = 0u;
     if (hit) {
         hit->last_use = ++g_pipe.graph_clock;
         count_launch();
         if (fail(cudaGraphLaunch(hit->exec, s0.stream), "cudaGraphLaunch")) return FEC_ERR_DEVICE;
-        return wait_stream(s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
+        return wait_flag(flag, s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
     }
-    auto launch = [&]() {
-        return is_u32 ? launch_viterbi_warp_u32((const uint32_t*)in, out, n, framebits, st->num_sms, s0.stream)
-                      : launch_viterbi_warp((const uint8_t*)in, out, n, framebits, st->num_sms, s0.stream);
-    };
+    auto launch = [&]() { return launch_viterbi_warp(in, out, n, framebits, st->num_sms, s0.stream, flag); };
     if (n == 1) {
         // first call of this shape: capture the launch into a graph and keep the executable
         cudaGraph_t graph = nullptr;
@@ -353,14 +368,16 @@ int dropin_launch(DeviceState* st, unsigned framebits, bool is_u32, const void* 
         (void)cudaGetLastError();
         if (ok) {
             if (victim->exec) cudaGraphExecDestroy(victim->exec);
-            *victim = DropinGraph{exec, framebits, is_u32, in, out, ++g_pipe.graph_clock};
+            *victim = DropinGraph{exec, framebits, in, out, flag, ++g_pipe.graph_clock};
             if (fail(cudaGraphLaunch(exec, s0.stream), "cudaGraphLaunch")) return FEC_ERR_DEVICE;
-            return wait_stream(s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
+            return wait_flag(flag, s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
         }
         // capture not possible (e.g. the host application is capturing globally): plain launch below
     }
     if (fail(launch(), "viterbi warp kernel launch")) return FEC_ERR_DEVICE;
-    return wait_stream(s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
+    // a batch raises the flag once per block, so only the stream tells when all of them are done
+    if (n > 1) return wait_stream(s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
+    return wait_flag(flag, s0.stream, "drop-in decode") ? FEC_OK : FEC_ERR_DEVICE;
 }
 
 // Host-pointer batch: chunks pipelined over kPipe streams (H2D | kernel | D2H overlap).
@@ -396,28 +413,40 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
     }
     // Small calls (the single-frame drop-in above all) bounce through this thread's pinned buffer: the driver's
     // pageable-copy path serialises concurrent callers (4 threads at F=3072 were slower than 1), a 50 KB memcpy
-    // into pinned memory does not.
+    // into pinned memory does not.  QIRX's one-word-per-symbol layout is compacted to bytes by that very copy
+    // (only the low byte counts: deconvolve.cpp:219-228), so a quarter of the bytes cross PCIe.
     uint8_t* bounce_out = nullptr;
     uint8_t* const user_out = out;
     const size_t in_bytes = n * in_row, out_bytes = n * nout;
     if (in_bytes + out_bytes <= kBounceBytes) {
         Slot& s0 = g_pipe.slot[0];
-        const size_t in_pad = (in_bytes + 255) & ~(size_t)255;
-        if (s0.pin_cap < in_pad + out_bytes) drop_graphs(g_pipe, true);  // the graphs point into the old buffer
-        if (!grow(&s0.h_pin, &s0.pin_cap, in_pad + out_bytes, true)) return FEC_ERR_DEVICE;
-        memcpy(s0.h_pin, syms, in_bytes);
+        const size_t in_keep = (is_u32 ? n * nsym : in_bytes), in_pad = (in_keep + 255) & ~(size_t)255;
+        const size_t out_pad = (out_bytes + 3) & ~(size_t)3;
+        if (s0.pin_cap < in_pad + out_pad + 4) drop_graphs(g_pipe, true);  // the graphs point into the old buffer
+        if (!grow(&s0.h_pin, &s0.pin_cap, in_pad + out_pad + 4, true)) return FEC_ERR_DEVICE;
+        if (is_u32) {
+            const uint32_t* src = static_cast<const uint32_t*>(syms);
+            uint8_t* dst = static_cast<uint8_t*>(s0.h_pin);
+            for (size_t i = 0; i < n * nsym; i++) dst[i] = (uint8_t)src[i];
+        } else if (syms != s0.h_pin) {  // (the u32 case below re-enters with the compacted buffer itself)
+            memcpy(s0.h_pin, syms, in_bytes);
+        }
         syms = s0.h_pin;
         bounce_out = (uint8_t*)s0.h_pin + in_pad;
         out = bounce_out;
-    }
-    // ... and when the warp-per-frame kernel would decode them anyway, it runs directly on the bounce buffer:
-    // pinned memory is mapped into the device's address space, the kernel stages the symbols into shared memory
-    // itself (compacting the u32 layout on the way) and writes the decoded bytes back through the mapping, so
-    // the call is one (graph) launch and one wait -- no copy operations, no compaction kernel.
-    if (bounce_out && !punct && n < kVitWarpKernelMaxFrames && g_vit_kernel.load() != FEC_VITERBI_PAIR) {
-        const int rc = dropin_launch(st, framebits, is_u32, syms, bounce_out, n);
-        if (rc == FEC_OK) memcpy(user_out, bounce_out, out_bytes);
-        return rc;
+        // ... and when the warp-per-frame kernel would decode them anyway, it runs directly on the bounce buffer:
+        // pinned memory is mapped into the device's address space, the kernel stages the symbols into shared
+        // memory itself, writes the decoded bytes back through the mapping and raises a completion flag behind
+        // them, so the call is one (graph) launch and one poll -- no copy operations, no synchronise.
+        if (!punct && n < kVitWarpKernelMaxFrames && g_vit_kernel.load() != FEC_VITERBI_PAIR) {
+            const int rc = dropin_launch(st, framebits, (const uint8_t*)syms, bounce_out,
+                                         reinterpret_cast<uint32_t*>(bounce_out + out_pad), n);
+            if (rc == FEC_OK) memcpy(user_out, bounce_out, out_bytes);
+            return rc;
+        }
+        if (is_u32) {  // compacted already: the rest of the path sees the byte layout
+            return vit_host(framebits, syms, SymFormat::U8, n, user_out);
+        }
     }
     // chunks are pipelined over kPipe streams: the H2D copy of chunk k+1, the kernel of chunk k and the
     // D2H copy of chunk k-1 overlap

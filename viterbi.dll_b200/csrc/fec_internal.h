@@ -22,6 +22,7 @@ constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision
 // and ~600 warps to fill the device).  Measured crossover (profiles/kernel_crossover_r01.jsonl):
 // between 4,096 and 8,192 frames at F=768, between 2,048 and 4,096 at F=3072.
 constexpr unsigned long long kVitWarpKernelMaxFrames = 4096;
+constexpr int kVitWarpThreads = 128;  // warp-per-frame kernel: warp 0 runs the trellis, all four stage / collect
 constexpr int kRsThreads = 128;
 constexpr uint32_t kMaxFramebits = 9216;  // decision array bound of the reference, deconvolve.cpp:127
 constexpr uint32_t kRsMaxDims = 1024;     // one superframe must fit a shared-memory tile (120 KB)
@@ -34,10 +35,9 @@ size_t viterbi_warp_smem_bytes(uint32_t framebits);
 cudaError_t viterbi_configure_device();
 cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_scratch, unsigned long long nframes,
                                 uint32_t framebits, int grid_blocks, cudaStream_t stream);
+// done_flag (optional, host-mapped): set to 1 by the kernel once its output is visible to the host
 cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
-                                int num_sms, cudaStream_t stream);
-cudaError_t launch_viterbi_warp_u32(const uint32_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
-                                    int num_sms, cudaStream_t stream);
+                                int num_sms, cudaStream_t stream, uint32_t* done_flag = nullptr);
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
                               uint32_t erasure, uint8_t* d_syms, size_t nframes, int num_sms, cudaStream_t stream);
 cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t nsymbols, int num_sms,

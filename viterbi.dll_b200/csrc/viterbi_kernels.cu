@@ -206,223 +206,6 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Latency / small-batch kernel: one warp per frame, two path metrics per lane, survivor decisions as warp
-// ballots in shared memory, traceback out of shared memory -- decisions never leave the SM.  This is the
-// layout of the design brief, tuned for the length of the per-step dependency chain, which is all that matters
-// when one warp runs alone on an SM sub-partition (the single-frame drop-in call):
-//
-//   * ONE shuffle per trellis step.  The 6 state bits are spread over 5 lane bits and 1 "slot" bit (which of the
-//     lane's two registers).  A butterfly needs the two old states that differ in state bit 5 in one lane and
-//     produces the two new states that differ in bit 0, so after a butterfly the slot holds bit 0 and some lane
-//     bit holds the new bit 5.  Instead of restoring a fixed layout (two shuffles of a packed pair plus
-//     pack/unpack, as the first version of this kernel did), the assignment of state bits to lane bits rotates:
-//     one shfl.xor across exactly that lane bit swaps it with the slot -- each lane keeps one of its two new
-//     metrics and trades the other with its partner.  Before butterfly t lane bit l holds state bit
-//     (l + t) mod 5, the exchange after it crosses lane bit 4 - (t mod 5), the period is 5 steps.
-//     The butterfly index of a lane is rotl5(lane, t mod 5), so its branch mask is one of five per-lane constants.
-//   * The serial chain per step is select -> shuffle -> select -> add-min -> min (about 40 cycles); the branch
-//     metric of the step (a dot-product form of the reference's two-level pavgb, see branch_metric_dp), the
-//     ballots, the renormalisation test and the decision store hang off it.
-//   * Traceback runs in "lane coordinates" (which lane / slot holds the current state), where one step is a
-//     rotate and a bit-select: the decision words are stored pre-rotated so that the decision bit lands on the
-//     lane bit it replaces.  The decoded bits are collected afterwards by the whole warp.
-// ~34 warp-instructions per trellis step against 6.5 per frame-step for the pair kernel, so it is used where the
-// pair kernel cannot fill the machine: the single-frame drop-in call and batches below kVitWarpKernelMaxFrames.
-// ---------------------------------------------------------------------------------------------------
-namespace {
-
-// Branch metric of deconvolve.cpp:338-349, m = avg(avg(x0,x1), avg(x2,x3)) >> 2 with avg(a,b) = (a+b+1) >> 1,
-// without the two-level rounding: with S = x0+x1+x2+x3 and q = lsb(x0^x1) + lsb(x2^x3) it equals
-// (S + 2 + q) >> 4 (each first-level average rounds up exactly when its two bytes differ in parity), which is
-// two byte dot-products (tests/test_device_code_on_host.py checks the identity exhaustively per byte pair).
-__device__ __forceinline__ uint32_t branch_metric_dp(uint32_t w, uint32_t xmask) {
-    const uint32_t x = w ^ xmask;
-    const uint32_t s = __dp4a(x, 0x01010101u, 2u);
-    const uint32_t par = (x ^ (x >> 8)) & 0x00010001u;
-    return __dp4a(par, 0x01010101u, s) >> 4;
-}
-
-__device__ __forceinline__ uint32_t rotl5(uint32_t v, uint32_t r) { return ((v << r) | (v >> (5u - r))) & 31u; }
-
-// One trellis step of the warp kernel.  kPhase = t mod 5, kOdd = t & 1 (the renormalisation test follows odd
-// steps: deconvolve.cpp:407-412).  A / B: the lane's old states with state bit 5 = 0 / 1.
-template <int kPhase, bool kOdd>
-__device__ __forceinline__ void warp_step(uint32_t& A, uint32_t& B, uint32_t w, uint32_t xmask, uint32_t lane,
-                                          uint2* dec_slot) {
-    constexpr uint32_t kFull = 0xffffffffu;
-    constexpr int kLaneBit = 4 - kPhase;            // lane bit that holds the new state bit 5
-    constexpr int kPrevBit = (5 - kPhase) % 5;      // lane bit the exchange before this butterfly crossed
-    const uint32_t m = branch_metric_dp(w, xmask), mm = 63u - m;
-    // ACS (deconvolve.cpp:352-359); ties choose the upper predecessor (decision = 1)
-    bool pe, po;
-    const uint32_t ne = __vibmin_u32(__viaddmin_u32(B, mm, 255u), A + m, &pe);
-    const uint32_t no = __vibmin_u32(__viaddmin_u32(B, m, 255u), A + mm, &po);
-    const bool up = (lane >> kLaneBit) & 1u;
-    const uint32_t recv = __shfl_xor_sync(kFull, up ? ne : no, 1u << kLaneBit);
-    const uint32_t keep = up ? no : ne;
-    uint32_t n0 = 0;
-    if (kOdd) n0 = __shfl_sync(kFull, ne, 0);  // new state 0 always lives in lane 0, slot 0
-    const uint32_t be = __ballot_sync(kFull, pe), bo = __ballot_sync(kFull, po);
-    A = up ? recv : keep;
-    B = up ? keep : recv;
-    if (kOdd) {  // Renormalize256: metric[state 0] > 150 -> all metrics -= 63, clamped at 0
-        const int neg = n0 > 150u ? -63 : 0;
-        A = (uint32_t)__viaddmax_s32_relu((int)A, neg, 0);
-        B = (uint32_t)__viaddmax_s32_relu((int)B, neg, 0);
-    }
-    // decision of the new state in (lane l, slot e/o) is bit l of be / bo; stored rotated left by kPrevBit so that
-    // the traceback's rotate-right by its lane number drops the bit onto lane bit kPrevBit
-    if (lane == 0) *dec_slot = make_uint2(__funnelshift_l(be, be, kPrevBit), __funnelshift_l(bo, bo, kPrevBit));
-}
-
-// One traceback step in lane coordinates: (ln, w) = lane number of the current state and the decision word of
-// its slot.  The predecessor keeps the lane (a butterfly is lane-local) with slot = the decision; undoing the
-// exchange before the butterfly swaps that slot with lane bit kPrevBit.
-template <int kPrevBit>
-__device__ __forceinline__ void warp_trace_step(uint32_t& ln, uint32_t& w, const uint2 next, uint32_t* x_slot) {
-    const uint32_t x = __funnelshift_r(w, w, ln);       // decision bit of lane ln -> bit kPrevBit
-    w = (ln >> kPrevBit) & 1u ? next.y : next.x;         // slot of the predecessor = the lane bit it replaces
-    *x_slot = x;
-    ln = (ln & ~(1u << kPrevBit)) | (x & (1u << kPrevBit));
-}
-
-}  // namespace
-
-// kU32: the symbols arrive in QIRX's one-uint32-per-symbol layout (low byte used, deconvolve.cpp:219-228) and are
-// compacted while they are staged.  The decoded bytes are collected in shared memory and written out by the
-// whole warp, so both ends work on host-mapped (pinned) memory as well: the single-frame drop-in call runs this
-// kernel straight on the caller's bounce buffer, with no copy operations around it.
-template <bool kU32>
-__global__ void __launch_bounds__(32) viterbi_warp_kernel(const void* __restrict__ syms_any, uint8_t* __restrict__ out,
-                                                          unsigned long long nframes, uint32_t framebits) {
-    extern __shared__ __align__(16) uint8_t wsmem[];
-    const uint32_t steps = framebits + 6, lane = threadIdx.x;
-    uint32_t* s_sym = reinterpret_cast<uint32_t*>(wsmem);         // [steps] 4 symbols per step; reused by the traceback
-    uint2* s_dec = reinterpret_cast<uint2*>(wsmem + 4 * (size_t)steps);  // [steps] rotated {even, odd} ballots
-    const size_t outbytes = (framebits + 7) / 8;
-
-    // branch masks (const.asm:35-49 restated: 0xFF where the expected code bit is 1) of the five butterflies
-    // this lane runs in turn: index rotl5(lane, t mod 5)
-    uint32_t xm[5];
-#pragma unroll
-    for (uint32_t r = 0; r < 5; r++) {
-        const uint32_t i = r ? rotl5(lane, r) : lane;
-        xm[r] = (parity8((2u * i) & kPoly(0)) ? 0xFF0000FFu : 0u) |  // polys 0 and 3 coincide
-                (parity8((2u * i) & kPoly(1)) ? 0x0000FF00u : 0u) | (parity8((2u * i) & kPoly(2)) ? 0x00FF0000u : 0u);
-    }
-
-    for (unsigned long long f = blockIdx.x; f < nframes; f += gridDim.x) {
-        __syncwarp();
-        if (kU32) {
-            const uint4* row = reinterpret_cast<const uint4*>(syms_any) + f * (size_t)steps;  // one step per uint4
-            // eight loads in flight per lane: over PCIe (host-mapped input) each round trip costs ~1.5 us
-            for (uint32_t i0 = lane; i0 < steps; i0 += 32 * 8) {
-                uint4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (i0 + 32 * u < steps) v[u] = __ldg(row + i0 + 32 * u);
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (i0 + 32 * u < steps)
-                        s_sym[i0 + 32 * u] = (v[u].x & 0xFFu) | ((v[u].y & 0xFFu) << 8) | ((v[u].z & 0xFFu) << 16) | (v[u].w << 24);
-            }
-        } else {
-            const uint2* row = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(syms_any) + f * 4 * (size_t)steps);
-            for (uint32_t i0 = lane; i0 < steps / 2; i0 += 32 * 8) {
-                uint2 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (i0 + 32 * u < steps / 2) v[u] = __ldg(row + i0 + 32 * u);
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (i0 + 32 * u < steps / 2) reinterpret_cast<uint2*>(s_sym)[i0 + 32 * u] = v[u];
-            }
-        }
-        __syncwarp();
-
-        // ---- forward pass: ten steps per iteration (period 5 of the layout x period 2 of the renormalisation) ----
-        uint32_t A = (lane == 0) ? 0u : 63u, B = 63u;  // Locals256: M[0] = 0, others 63 (deconvolve.cpp:130-132)
-        uint32_t t = 0;
-        for (; t + 10 <= steps; t += 10) {
-            uint32_t w[10];
-#pragma unroll
-            for (int u = 0; u < 10; u++) w[u] = s_sym[t + u];
-            warp_step<0, false>(A, B, w[0], xm[0], lane, s_dec + t + 0);
-            warp_step<1, true>(A, B, w[1], xm[1], lane, s_dec + t + 1);
-            warp_step<2, false>(A, B, w[2], xm[2], lane, s_dec + t + 2);
-            warp_step<3, true>(A, B, w[3], xm[3], lane, s_dec + t + 3);
-            warp_step<4, false>(A, B, w[4], xm[4], lane, s_dec + t + 4);
-            warp_step<0, true>(A, B, w[5], xm[0], lane, s_dec + t + 5);
-            warp_step<1, false>(A, B, w[6], xm[1], lane, s_dec + t + 6);
-            warp_step<2, true>(A, B, w[7], xm[2], lane, s_dec + t + 7);
-            warp_step<3, false>(A, B, w[8], xm[3], lane, s_dec + t + 8);
-            warp_step<4, true>(A, B, w[9], xm[4], lane, s_dec + t + 9);
-        }
-        // the remaining 0, 2, ... 8 steps (steps is even): t is a multiple of 10 here
-        if (t < steps) {
-            warp_step<0, false>(A, B, s_sym[t + 0], xm[0], lane, s_dec + t + 0);
-            warp_step<1, true>(A, B, s_sym[t + 1], xm[1], lane, s_dec + t + 1);
-        }
-        if (t + 2 < steps) {
-            warp_step<2, false>(A, B, s_sym[t + 2], xm[2], lane, s_dec + t + 2);
-            warp_step<3, true>(A, B, s_sym[t + 3], xm[3], lane, s_dec + t + 3);
-        }
-        if (t + 4 < steps) {
-            warp_step<4, false>(A, B, s_sym[t + 4], xm[4], lane, s_dec + t + 4);
-            warp_step<0, true>(A, B, s_sym[t + 5], xm[0], lane, s_dec + t + 5);
-        }
-        if (t + 6 < steps) {
-            warp_step<1, false>(A, B, s_sym[t + 6], xm[1], lane, s_dec + t + 6);
-            warp_step<2, true>(A, B, s_sym[t + 7], xm[2], lane, s_dec + t + 7);
-        }
-        __syncwarp();
-
-        // ---- ChainBack (deconvolve.cpp:416-435) by lane 0, from state 0 (lane 0, slot 0) after the last step;
-        // the rotated decision word of every step replaces the symbol word of that step in s_sym -----------------
-        if (lane == 0 && framebits > 0) {
-            uint32_t ln = 0;
-            int tau = (int)steps - 1;  // decisions of steps 6 .. F+5 are consumed (t = tau - 6)
-            uint32_t w = s_dec[tau].x;
-            auto generic = [&](int tt) {  // one step with a run-time phase
-                const uint32_t pb = (5u - (uint32_t)tt % 5u) % 5u;
-                const uint2 next = s_dec[tt > 6 ? tt - 1 : tt];
-                const uint32_t x = __funnelshift_r(w, w, ln);
-                w = (ln >> pb) & 1u ? next.y : next.x;
-                s_sym[tt] = x;
-                ln = (ln & ~(1u << pb)) | (x & (1u << pb));
-            };
-            for (; tau >= 6 && tau % 5 != 4; tau--) generic(tau);
-            for (; tau >= 10; tau -= 5) {  // tau % 5 == 4: the five records do not depend on the state
-                uint2 nx[5];
-#pragma unroll
-                for (int j = 0; j < 5; j++) nx[j] = s_dec[tau - 1 - j];
-                warp_trace_step<1>(ln, w, nx[0], s_sym + tau);
-                warp_trace_step<2>(ln, w, nx[1], s_sym + tau - 1);
-                warp_trace_step<3>(ln, w, nx[2], s_sym + tau - 2);
-                warp_trace_step<4>(ln, w, nx[3], s_sym + tau - 3);
-                warp_trace_step<0>(ln, w, nx[4], s_sym + tau - 4);
-            }
-            for (; tau >= 6; tau--) generic(tau);
-        }
-        __syncwarp();
-        // decoded bit t = the decision consumed at step t + 6 = bit (5 - (t+6) % 5) % 5 of its rotated word;
-        // output byte n holds bits 8n .. 8n+7, MSB first (missing bits of a ragged last byte stay 0)
-        for (uint32_t n = lane; n < outbytes; n += 32) {
-            uint32_t v = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < 8; j++) {
-                const uint32_t tb = 8 * n + j;
-                if (tb < framebits) {
-                    const uint32_t tt = tb + 6;
-                    v |= ((s_sym[tt] >> ((5u - tt % 5u) % 5u)) & 1u) << (7 - j);
-                }
-            }
-            out[f * outbytes + n] = (uint8_t)v;
-        }
-    }
-}
-
 // u32 -> u8 compaction for the QIRX one-word-per-symbol layout (low byte only, deconvolve.cpp:219-228)
 __global__ void __launch_bounds__(256) compact_symbols_kernel(const uint4* __restrict__ in, uint32_t* __restrict__ outw,
                                                               size_t nquads) {
@@ -488,41 +271,6 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
                                                                              framebits);
     count_launch();
     return cudaGetLastError();
-}
-
-size_t viterbi_warp_smem_bytes(uint32_t framebits) { return 12 * (size_t)(framebits + 6) + 16; }
-
-// The warp kernel needs more than 48 KB of dynamic shared memory above F = 4090.  The opt-in is a per-device
-// function attribute, so it is raised once per device to the worst case (F = 9216) from the device
-// initialisation in fec_api.cu -- not lazily per launch, where concurrent callers with different frame sizes
-// would lower each other's limit.
-cudaError_t viterbi_configure_device() {
-    const int worst = (int)viterbi_warp_smem_bytes(kMaxFramebits);
-    cudaError_t e = cudaFuncSetAttribute(viterbi_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, worst);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(viterbi_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, worst);
-}
-
-template <bool kU32>
-static cudaError_t launch_viterbi_warp_t(const void* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
-                                         int num_sms, cudaStream_t stream) {
-    if (nframes == 0) return cudaSuccess;
-    const size_t smem = viterbi_warp_smem_bytes(framebits);
-    const unsigned long long cap = (unsigned long long)num_sms * 32;
-    const unsigned grid = (unsigned)(nframes < cap ? nframes : cap);
-    viterbi_warp_kernel<kU32><<<grid, 32, smem, stream>>>(d_syms, d_out, nframes, framebits);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
-                                int num_sms, cudaStream_t stream) {
-    return launch_viterbi_warp_t<false>(d_syms, d_out, nframes, framebits, num_sms, stream);
-}
-
-cudaError_t launch_viterbi_warp_u32(const uint32_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
-                                    int num_sms, cudaStream_t stream) {
-    return launch_viterbi_warp_t<true>(d_syms, d_out, nframes, framebits, num_sms, stream);
 }
 
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
