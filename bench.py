@@ -682,12 +682,16 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
 
     f, s = 3072, 16
     total_sf = args.configs4_frames // 5
-    res_sf_cap = (1 << 21) // 5
+    res_sf_cap = -(-(1 << 21) // 5)  # 2^21 frames of symbols (25.8 GB) resident per GPU
     my_sf = -(-total_sf // world)
-    chunks_resident = 4
-    chunk_sf = -(-min(my_sf, res_sf_cap) // chunks_resident)
-    rounds = -(-my_sf // chunk_sf)
-    res_sf = chunk_sf * min(chunks_resident, rounds)
+    # one round = one launch per rank.  Large launches lose the least to the tail of the persistent grid, but the
+    # gather of the LAST round cannot overlap anything, so a rank's share is cut into at least four rounds
+    # (N = 8: four rounds of 2^19 frames; N = 1: eight resident passes of 2^21 frames).
+    passes = -(-my_sf // res_sf_cap)
+    rounds = max(4, passes)
+    chunk_sf = -(-my_sf // rounds)
+    chunks_resident = max(1, min(rounds, res_sf_cap // chunk_sf))
+    res_sf = chunk_sf * chunks_resident
     job_sf = rounds * world * chunk_sf  # superframes actually decoded (>= total_sf: the last round is padded)
     t0 = time.perf_counter()
     syms, payload = dabgen.make_superframe_frames_torch(res_sf, f, 4.0, seed=5000 + 17 * rank, device=dev, max_err=3)
@@ -706,7 +710,7 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
             st.wait_stream(main)
         for j in range(rounds):
             st = comp[j % 2]
-            c = j % chunks_resident if rounds >= chunks_resident else j
+            c = j % chunks_resident
             vb.dabplus_decode_superframes_device(f, syms[c * chunk_sf * 5:(c + 1) * chunk_sf * 5], allout[j, rank], allret[j, rank], st)
             if gather and world > 1:
                 done = torch.cuda.Event()
@@ -736,7 +740,7 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     # what that rank decoded; a slice is compared bit for bit with the CPU reference chain ------------------------
     run_job(True)
     mine_out, mine_ret = allout[:, rank], allret[:, rank]
-    nres = min(rounds, chunks_resident)
+    nres = chunks_resident
     ok = mine_ret[:nres] >= 0
     pay = payload.view(nres, chunk_sf, 110 * s)
     wrong = int((mine_out[:nres][ok] != pay[ok]).any(dim=1).sum().item())

@@ -50,6 +50,7 @@ __device__ RsTables c_tables;
 __shared__ uint4 s_lfsr[256];
 __shared__ uint8_t s_ato[768];
 __shared__ uint8_t s_iof[256];
+__shared__ int s_nfail;  // failing superframes of the current tile (host path that merges the caller's bytes)
 // The per-codeword decoder lives in rs_decode.h (shared with the host check of the CPU suite); this is its device
 // policy: tables in shared memory, warp votes.
 struct DevicePolicy {
@@ -148,35 +149,78 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                 if (fail > 0)
                     for (uint32_t i = tid; i < (uint32_t)sf_out; i += blockDim.x)
                         if (i - __umulhi(i, inv_s) * s < fail) d[i] = t[i];
-            } else {
-                // Host path without an upload of the caller's outVector: `out` is a staging buffer that is copied
-                // back whole, so every byte of the row is produced here -- decoded columns from the tile, the
-                // untouched ones (rschecksf.cpp:85-88) from the caller's own bytes, read through the device mapping
-                // of the caller's pinned buffer.  Only failing superframes read it: aligned 32-bit loads, so a warp
-                // asks for whole 128-byte lines across PCIe.
-                const uint8_t* o = orig + (sf0 + n) * sf_out;
-                const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3);
-                const uint32_t nhead = head < sf_out ? head : (uint32_t)sf_out;
-                auto col = [&](uint32_t i) { return i - __umulhi(i, inv_s) * s; };
-                if (tid < nhead) d[tid] = col(tid) < fail ? t[tid] : o[tid];
-                const uint32_t nwords = (uint32_t)((sf_out - nhead) / 4);
-                const uint32_t toff = (uint32_t)(reinterpret_cast<uintptr_t>(t + nhead) & 3);
-                const uint32_t* tw = reinterpret_cast<const uint32_t*>(t + nhead - toff);
-                const uint32_t tsel = 0x3210u + 0x1111u * toff;
-                const uint32_t ooff = (uint32_t)(reinterpret_cast<uintptr_t>(o + nhead) & 3);
-                const uint32_t* ow = reinterpret_cast<const uint32_t*>(o + nhead - ooff);
-                const uint32_t osel = 0x3210u + 0x1111u * ooff;
-                for (uint32_t w = tid; w < nwords; w += blockDim.x) {
-                    // the second word is only touched when it holds a byte of this row (never past the caller's array)
-                    const uint32_t o0 = ow[w], o1 = ooff ? ow[w + 1] : 0u;
-                    const uint32_t ov = __byte_perm(o0, o1, osel), tv = __byte_perm(tw[w], tw[w + 1], tsel);
-                    const uint32_t i0 = nhead + 4 * w;
-                    const uint32_t keep = (col(i0) < fail ? 0x000000FFu : 0u) | (col(i0 + 1) < fail ? 0x0000FF00u : 0u) |
-                                          (col(i0 + 2) < fail ? 0x00FF0000u : 0u) | (col(i0 + 3) < fail ? 0xFF000000u : 0u);
-                    reinterpret_cast<uint32_t*>(d + nhead)[w] = (tv & keep) | (ov & ~keep);
+            }
+        }
+        if (orig != nullptr) {
+            // Host path without an upload of the caller's outVector: `out` is a staging buffer that is copied
+            // back whole, so every byte of a failing superframe's row is produced here -- decoded columns from
+            // the tile, the untouched ones (rschecksf.cpp:85-88) from the caller's own bytes, read through the
+            // device mapping of the caller's pinned buffer (aligned 32-bit loads: a warp asks for whole 128-byte
+            // lines across PCIe).  All failing superframes of the tile are handled in ONE flat loop over
+            // (superframe, 4-byte slot) pairs, four slots per thread at a time with their loads issued together:
+            // a PCIe round trip costs ~2 us, and one at a time per superframe they would serialise.
+            __syncthreads();  // s_sum has been consumed by the return values: it now holds the list of failing superframes
+            if (tid == 0) s_nfail = 0;
+            __syncthreads();
+            for (uint32_t n = tid; n < nloc; n += blockDim.x)
+                if ((uint32_t)s_fail[n] < s) s_sum[atomicAdd(&s_nfail, 1)] = (int)n;
+            __syncthreads();
+            const uint32_t slots = (uint32_t)sf_out / 4 + 2;  // per superframe: head bytes, the aligned words, tail bytes
+            const uint32_t inv_slots = (uint32_t)((0x100000000ull + slots - 1) / slots);
+            const uint32_t total = (uint32_t)s_nfail * slots;
+            auto col = [&](uint32_t i) { return i - __umulhi(i, inv_s) * s; };
+            constexpr int kBatch = 4;
+            for (uint32_t f0 = tid; f0 < total; f0 += blockDim.x * kBatch) {
+                uint32_t sn[kBatch], sj[kBatch], o0[kBatch], o1[kBatch];
+#pragma unroll
+                for (int q = 0; q < kBatch; q++) {  // stage 1: which slot, and its load(s) of the caller's bytes
+                    const uint32_t fl = f0 + q * blockDim.x;
+                    o0[q] = o1[q] = 0u;
+                    sn[q] = 0xFFFFFFFFu;
+                    if (fl < total) {
+                        const uint32_t li = __umulhi(fl, inv_slots);
+                        const uint32_t n = (uint32_t)s_sum[li], j = fl - li * slots;
+                        const uint8_t* dd = dst + n * sf_out;
+                        const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dd) & 3)) & 3);
+                        const uint32_t nhead = head < sf_out ? head : (uint32_t)sf_out;
+                        const uint32_t nwords = (uint32_t)((sf_out - nhead) / 4);
+                        sn[q] = n, sj[q] = j;
+                        if (j >= 1 && j <= nwords) {
+                            const uint8_t* o = orig + (sf0 + n) * sf_out + nhead;
+                            const uint32_t ooff = (uint32_t)(reinterpret_cast<uintptr_t>(o) & 3);
+                            const uint32_t* ow = reinterpret_cast<const uint32_t*>(o - ooff) + (j - 1);
+                            // the second word is only touched when it holds a byte of this row (never past the caller's array)
+                            o0[q] = __ldg(ow);
+                            if (ooff) o1[q] = __ldg(ow + 1);
+                        }
+                    }
                 }
-                for (uint32_t i = nhead + nwords * 4 + tid; i < (uint32_t)sf_out; i += blockDim.x)
-                    d[i] = col(i) < fail ? t[i] : o[i];
+#pragma unroll
+                for (int q = 0; q < kBatch; q++) {  // stage 2: merge and store
+                    if (sn[q] == 0xFFFFFFFFu) continue;
+                    const uint32_t n = sn[q], j = sj[q], fail = (uint32_t)s_fail[n];
+                    const uint8_t* t = tile + n * sf_in;
+                    uint8_t* dd = dst + n * sf_out;
+                    const uint8_t* o = orig + (sf0 + n) * sf_out;
+                    const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dd) & 3)) & 3);
+                    const uint32_t nhead = head < sf_out ? head : (uint32_t)sf_out;
+                    const uint32_t nwords = (uint32_t)((sf_out - nhead) / 4);
+                    if (j == 0) {
+                        for (uint32_t i = 0; i < nhead; i++) dd[i] = col(i) < fail ? t[i] : __ldg(o + i);
+                    } else if (j <= nwords) {
+                        const uint32_t w = j - 1, i0 = nhead + 4 * w;
+                        const uint32_t toff = (uint32_t)(reinterpret_cast<uintptr_t>(t + nhead) & 3);
+                        const uint32_t* tw = reinterpret_cast<const uint32_t*>(t + nhead - toff);
+                        const uint32_t ooff = (uint32_t)(reinterpret_cast<uintptr_t>(o + nhead) & 3);
+                        const uint32_t tv = __byte_perm(tw[w], tw[w + 1], 0x3210u + 0x1111u * toff);
+                        const uint32_t ov = __byte_perm(o0[q], o1[q], 0x3210u + 0x1111u * ooff);
+                        const uint32_t keep = (col(i0) < fail ? 0x000000FFu : 0u) | (col(i0 + 1) < fail ? 0x0000FF00u : 0u) |
+                                              (col(i0 + 2) < fail ? 0x00FF0000u : 0u) | (col(i0 + 3) < fail ? 0xFF000000u : 0u);
+                        reinterpret_cast<uint32_t*>(dd + nhead)[w] = (tv & keep) | (ov & ~keep);
+                    } else if (j == nwords + 1) {
+                        for (uint32_t i = nhead + nwords * 4; i < (uint32_t)sf_out; i++) dd[i] = col(i) < fail ? t[i] : __ldg(o + i);
+                    }
+                }
             }
         }
     }
