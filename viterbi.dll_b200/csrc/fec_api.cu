@@ -32,6 +32,7 @@ constexpr int kMaxDevices = 64;
 constexpr int kPipe = 3;  // host-path pipeline depth (streams / staging slots)
 constexpr size_t kBounceBytes = 256 * 1024;  // calls moving less than this bounce through pinned memory
 constexpr size_t kTrimBytes = (size_t)768 << 20;  // staging buffers above this are released when the call returns
+constexpr float kRsFetchMaxFailFrac = 0.55f;  // above this share of failing superframes outVector is uploaded instead
 constexpr int kGraphCache = 4;  // instantiated single-kernel graphs kept per calling thread (drop-in path)
 
 std::atomic<unsigned long long> g_launches{0};
@@ -84,6 +85,7 @@ struct HostPipe {
     cudaEvent_t idx_ready = nullptr;
     DropinGraph graph[kGraphCache];
     unsigned long long graph_clock = 0;
+    float rs_fail_frac = -1.0f;  // running failure fraction of this thread's RS batches (-1: nothing observed yet)
     ~HostPipe();
 };
 thread_local HostPipe g_pipe;
@@ -507,6 +509,11 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
 // Device pointer through which a kernel can read the caller's host buffer directly, or nullptr when the buffer is
 // ordinary pageable memory (pinned memory -- fec_host_alloc(), cudaMallocHost, cudaHostRegister -- is mapped).
 const uint8_t* mapped_host_pointer(const void* p) {
+    static const bool never = [] {  // VITERBI_B200_RS_UPLOAD=1: always upload outVector (A/B measurements)
+        const char* env = getenv("VITERBI_B200_RS_UPLOAD");
+        return env && *env == '1';
+    }();
+    if (never) return nullptr;
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -547,25 +554,40 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
         return FEC_OK;
     }
     // The partial-write rule (rschecksf.cpp:80-88) leaves the columns from the first failing one on untouched, so
-    // the result rows are a merge of decoded bytes and the caller's current outVector bytes.  When outVector is
-    // pinned the kernel fetches the caller's bytes of FAILING superframes itself through the buffer's device
-    // mapping and produces complete rows, which are copied back whole; otherwise outVector is uploaded first.
+    // the result rows are a merge of decoded bytes and the caller's current outVector bytes.  Two ways to get the
+    // caller's bytes to the device: upload outVector ahead of the kernel (DMA, all rows), or -- when outVector is
+    // pinned -- let the kernel fetch the rows of FAILING superframes itself through the buffer's device mapping.
+    // Measured (profiles/rs_e2e_ab.py): with no failures the second is 1.56x faster end to end (67 vs 43 M
+    // superframes/s on the s = 1..8 mix: 0.46x the bytes cross PCIe), but kernel reads reach only ~85 % of the DMA
+    // rate, so above ~55 % failing superframes the upload wins.  The choice is made per chunk from the failure
+    // fraction of the chunks already returned (carried over between calls of the same thread).
     const uint8_t* d_orig_base = mapped_host_pointer(out);
     size_t chunk = rs_chunk_bytes() / in_row;
     if (chunk < 1) chunk = 1;
     if (chunk > n) chunk = n;
     int rc = FEC_OK;
     size_t done = 0;
+    size_t slot_first[kPipe] = {0}, slot_count[kPipe] = {0};  // superframes whose return values a slot last produced
+    auto observe = [&](int k) {  // the slot's stream has been synchronised: its return values are in `ret`
+        if (!slot_count[k]) return;
+        size_t failed = 0;
+        for (size_t i = 0; i < slot_count[k]; i++) failed += ret[slot_first[k] + i] < 0;
+        const float frac = (float)failed / (float)slot_count[k];
+        g_pipe.rs_fail_frac = g_pipe.rs_fail_frac < 0 ? frac : 0.5f * g_pipe.rs_fail_frac + 0.5f * frac;
+        slot_count[k] = 0;
+    };
     for (int k = 0; done < n && rc == FEC_OK; k++) {
         Slot& sl = g_pipe.slot[k % kPipe];
         const size_t m = (n - done < chunk) ? n - done : chunk;
         if (fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize")) { rc = FEC_ERR_DEVICE; break; }
+        observe(k % kPipe);
         if (!grow(&sl.d_in, &sl.in_cap, m * in_row) || !grow(&sl.d_out, &sl.out_cap, m * out_row) ||
             !grow(&sl.d_aux, &sl.aux_cap, m * sizeof(int32_t))) {
             rc = FEC_ERR_DEVICE;
             break;
         }
-        const uint8_t* d_orig = d_orig_base ? d_orig_base + done * out_row : nullptr;
+        const bool fetch = d_orig_base && g_pipe.rs_fail_frac < kRsFetchMaxFailFrac;
+        const uint8_t* d_orig = fetch ? d_orig_base + done * out_row : nullptr;
         if (fail(cudaMemcpyAsync(sl.d_in, in + done * in_row, m * in_row, cudaMemcpyHostToDevice, sl.stream), "H2D") ||
             (!d_orig && fail(cudaMemcpyAsync(sl.d_out, out + done * out_row, m * out_row, cudaMemcpyHostToDevice, sl.stream), "H2D out")) ||
             fail(launch_rs_superframes((const uint8_t*)sl.d_in, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux, d_orig, m, s,
@@ -576,10 +598,15 @@ int rs_host(const uint8_t* in, unsigned s, size_t n, uint8_t* out, int32_t* ret)
             rc = FEC_ERR_DEVICE;
             break;
         }
+        slot_first[k % kPipe] = done;
+        slot_count[k % kPipe] = m;
         done += m;
     }
-    for (Slot& sl : g_pipe.slot)
+    for (int k = 0; k < kPipe; k++) {
+        Slot& sl = g_pipe.slot[k];
         if (sl.stream && fail(cudaStreamSynchronize(sl.stream), "cudaStreamSynchronize") && rc == FEC_OK) rc = FEC_ERR_DEVICE;
+        if (rc == FEC_OK) observe(k);
+    }
     trim_pipe();
     return rc;
 }
