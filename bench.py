@@ -529,6 +529,37 @@ def run_b200(args):
         del msym, mout, mbits
         torch.cuda.empty_cache()
 
+        # the same FIC batches issued round-robin on two streams: a 65,536-frame batch is 1,024 warps on 592 SM
+        # sub-partitions (0.43 of the resident grid), so a single launch leaves issue slots idle -- at its tail and
+        # while all of its warps read their decisions back at once.  Consecutive batches on two streams fill them.
+        s2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        out2 = [out, torch.empty_like(out)]
+        for st_ in s2:
+            st_.wait_stream(stream)
+        def fic_two_streams(reps):
+            for i in range(reps):
+                vb.deconvolve_batch_device(f, syms, out2[i & 1], s2[i & 1])
+        fic_two_streams(4)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for st_ in s2:
+            st_.wait_stream(stream)
+        fic_two_streams(args.steps)
+        for st_ in s2:
+            stream.wait_stream(st_)
+        p1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms_pipe = reduce_ranks(p0.elapsed_time(p1)) / args.steps
+        if not torch.equal(out2[0], out2[1]):
+            parity["mismatches"] += 1
+        extra["fic_two_streams"] = {"workload": "the headline FIC batches, %d steps issued alternately on two streams (consecutive batches overlap on the device)" % args.steps,
+                                    "value": n * world * f / (ms_pipe * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": ms_pipe,
+                                    "roofline_issue_frac": (inst_per_gs * groups * steps_per_frame / (p0.elapsed_time(p1) / args.steps * 1e-3) / issue_peak)
+                                    if inst_per_gs else None}
+        del out2
+
         # single-frame drop-in latency (BASELINE configs[0]; viterbi-benchmark.cpp:332-348: repeated calls on one thread)
         if rank == 0:
             drop = {}
