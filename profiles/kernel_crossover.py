@@ -16,7 +16,7 @@ from viterbi_dll_b200 import dabgen  # noqa: E402
 
 assert vb.initialize()
 for f in (768, 3072):
-    for n in (64, 512, 2048, 4096, 8192, 16384, 32768, 65536):
+    for n in (1, 64, 296, 512, 1024, 2048, 4096, 6144, 8192, 12288, 16384, 32768, 65536):
         sym, _ = dabgen.make_frames_torch(n, f, 3.0, seed=1, device="cuda")
         out = torch.empty((n, f // 8), dtype=torch.uint8, device="cuda")
         row = {"framebits": f, "frames": n}

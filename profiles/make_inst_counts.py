@@ -44,14 +44,21 @@ def main():
         alu = alu_pct / 100.0 * 0.5 * cyc * 592  # the ALU pipe issues one warp-instruction every 2 cycles per sub-partition
     m = page(msc)
     m_inst, m_grid = num(m, "smsp__inst_executed.sum"), num(m, "launch__grid_size")
+    m_groups, m_steps = 262144 // 64, 3078  # the MSC page is bench.py's extra.msc workload
     out["viterbi_pair_kernel"] = {
         "warp_inst_per_group_step": inst / (groups * steps),
         "alu_pipe_inst_per_group_step": alu / (groups * steps) if alu else None,
+        "fmaheavy_pipe_inst_per_group_step": (num(f, "smsp__inst_executed_pipe_fmaheavy.sum") or 0) / (groups * steps) or None,
+        "fmalite_pipe_inst_per_group_step": (num(f, "smsp__inst_executed_pipe_fmalite.sum") or 0) / (groups * steps) or None,
+        "lsu_pipe_inst_per_group_step": (num(f, "smsp__inst_executed_pipe_lsu.sum") or 0) / (groups * steps) or None,
         "fic_launch": {"frames": 65536, "framebits": 768, "warp_inst": inst, "duration_us_under_ncu": num(f, "gpu__time_duration.sum"),
                        "registers": num(f, "launch__registers_per_thread"), "grid": num(f, "launch__grid_size"),
                        "issue_active_pct": num(f, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                        "alu_pipe_pct": alu_pct},
-        "msc_launch": {"warp_inst": m_inst, "grid": m_grid, "duration_us_under_ncu": num(m, "gpu__time_duration.sum"),
+        "msc_launch": {"frames": 262144, "framebits": 3072, "warp_inst": m_inst, "grid": m_grid,
+                       "warp_inst_per_group_step": m_inst / (m_groups * m_steps),
+                       "alu_pipe_inst_per_group_step": (num(m, "smsp__inst_executed_pipe_alu.sum") or 0) / (m_groups * m_steps) or None,
+                       "fmaheavy_pipe_inst_per_group_step": (num(m, "smsp__inst_executed_pipe_fmaheavy.sum") or 0) / (m_groups * m_steps) or None, "duration_us_under_ncu": num(m, "gpu__time_duration.sum"),
                        "registers": num(m, "launch__registers_per_thread"),
                        "issue_active_pct": num(m, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                        "alu_pipe_pct": num(m, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")},

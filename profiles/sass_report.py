@@ -53,9 +53,10 @@ def body_stats(ins, lo, hi):
     return body, hist
 
 
-def pair_kernel_loop(funcs, word_stores=True):
-    """The 2-step ACS loop of viterbi_pair_kernel<kWordStores>: the largest loop that contains VIADDMNMX.U16x2."""
-    name = next(n for n in funcs if "viterbi_pair_kernel" in n and ("ILb1E" in n) == word_stores)
+def pair_kernel_loop(funcs, word_stores=True, punctured=False):
+    """The 2-step ACS loop of viterbi_pair_kernel<kWordStores, kPunct>: the innermost loop that holds the butterflies."""
+    tag = "ILb%dELb%dE" % (int(word_stores), int(punctured))
+    name = next(n for n in funcs if "viterbi_pair_kernel" in n and tag in n)
     ins = funcs[name]
     best = None
     for lo, hi in loops(ins):
@@ -86,6 +87,10 @@ def summary(funcs=None):
         "function": name, "loop_instructions": len(body), "trellis_steps_per_iteration": 2,
         "instructions_per_step_64_frames": len(body) / 2.0, "vimnmx_u16x2_with_two_predicate_outputs": fused,
         "histogram": dict(hist.most_common())}
+    pname, pbody, phist = pair_kernel_loop(funcs, punctured=True)
+    res["viterbi_pair_kernel_punctured"] = {"function": pname, "loop_instructions": len(pbody),
+                                            "extra_instructions_vs_plain": len(pbody) - len(body),
+                                            "histogram": dict(phist.most_common())}
     name, wbody, whist = warp_kernel_loop(funcs)
     res["viterbi_warp_kernel"] = {"function": name, "loop_instructions": len(wbody), "trellis_steps_per_iteration": 10,
                                   "instructions_per_step": len(wbody) / 10.0, "histogram": dict(whist.most_common())}

@@ -96,7 +96,8 @@ def test_out_of_range_symbols_low_byte_only(vb, kernel, checker):
     assert rc == 0 and np.array_equal(out, want[3])
 
 
-@pytest.mark.parametrize("framebits,n,ebn0", [(768, 700, 4.0), (768, 5000, 5.0), (3072, 300, 4.0), (96, 130, 6.0)])
+@pytest.mark.parametrize("framebits,n,ebn0", [(768, 700, 4.0), (768, 5000, 5.0), (3072, 300, 4.0), (96, 130, 6.0), (770, 1, 4.0),
+                                              (768, 2, 4.0), (34, 65, 6.0)])
 def test_punctured_input_equals_reference_on_expanded_symbols(vb, kernel, checker, framebits, n, ebn0):
     """Depuncturing front end: decoding the transmitted symbols + keep pattern must equal the
     reference decoder run on the host-expanded rate-1/4 stream (erasures = 128), host and device flavours."""
@@ -108,6 +109,13 @@ def test_punctured_input_equals_reference_on_expanded_symbols(vb, kernel, checke
     patterns.append(dabgen.puncture_pattern(framebits, [(framebits // 32, 8)]))          # rate 1/2 everywhere
     patterns.append((rng.random(4 * (framebits + 6)) < 0.6).astype(np.uint8))           # arbitrary pattern
     patterns.append(np.ones(4 * (framebits + 6), np.uint8))                             # nothing punctured
+    sparse = (rng.random(4 * (framebits + 6)) < 0.12).astype(np.uint8)                  # whole steps without a symbol,
+    sparse[-40:] = 0                                                                    # ... nothing at all in the tail
+    sparse[5] = 1
+    patterns.append(sparse)
+    head = np.zeros(4 * (framebits + 6), np.uint8)
+    head[:17] = 1                                                                       # 17 symbols, then erasures only
+    patterns.append(head)
     for keep in patterns:
         rx = dabgen.puncture(sym, keep)
         for erasure in (128, 0):

@@ -80,7 +80,7 @@ struct HostPipe {
     int device = -1;
     unsigned generation = 0;
     Slot slot[kPipe];
-    void* d_idx = nullptr;  // depuncturing index table of the call in progress
+    void* d_idx = nullptr;  // depuncturing tables of the call in progress: [index table][per-iteration table]
     size_t idx_cap = 0;
     cudaEvent_t idx_ready = nullptr;
     DropinGraph graph[kGraphCache];
@@ -287,12 +287,17 @@ size_t rs_chunk_bytes() {
 
 bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= VITERBI_B200_MAX_FRAMEBITS; }
 
+// Does a launch of n frames go to the two-frames-per-thread throughput kernel (else: warp-per-frame kernel)?
+bool uses_pair_kernel(size_t n) {
+    const int mode = g_vit_kernel.load();
+    return mode == FEC_VITERBI_PAIR || (mode == FEC_VITERBI_AUTO && n >= kVitWarpKernelMaxFrames);
+}
+
 // Enqueue one batch that is already in device memory.  Scratch is stream-ordered.
 int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
                cudaStream_t stream, void* scratch, size_t scratch_cap) {
     if (n == 0 || framebits == 0) return FEC_OK;
-    const int mode = g_vit_kernel.load();
-    if (mode == FEC_VITERBI_WARP || (mode == FEC_VITERBI_AUTO && n < kVitWarpKernelMaxFrames))
+    if (!uses_pair_kernel(n))
         // latency / small-batch path: decisions stay in shared memory
         return fail(launch_viterbi_warp(d_syms, d_out, n, framebits, st->num_sms, stream), "viterbi warp kernel launch")
                    ? FEC_ERR_DEVICE
@@ -303,6 +308,20 @@ int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_
     const bool own = (ws == nullptr) || scratch_cap < need;
     if (own && fail(cudaMallocAsync(&ws, need, stream), "cudaMallocAsync(scratch)")) return FEC_ERR_DEVICE;
     cudaError_t e = launch_viterbi_pair(d_syms, d_out, ws, n, framebits, blocks, stream);
+    if (own) (void)cudaFreeAsync(ws, stream);
+    return fail(e, "viterbi kernel launch") ? FEC_ERR_DEVICE : FEC_OK;
+}
+
+// Punctured rows that are already in device memory (followed by kPunctSlackBytes readable bytes): the throughput
+// kernel expands them in its symbol fetch.  d_ptab: punct_table() on the device.
+int vit_device_punctured(DeviceState* st, unsigned framebits, const uint8_t* d_rx, size_t rx_per_frame, const void* d_ptab,
+                         unsigned erasure, size_t n, uint8_t* d_out, cudaStream_t stream, void* scratch, size_t scratch_cap) {
+    const int blocks = viterbi_grid_blocks(st->num_sms, n, framebits);
+    const size_t need = viterbi_scratch_bytes(blocks, framebits);
+    void* ws = scratch;
+    const bool own = (ws == nullptr) || scratch_cap < need;
+    if (own && fail(cudaMallocAsync(&ws, need, stream), "cudaMallocAsync(scratch)")) return FEC_ERR_DEVICE;
+    cudaError_t e = launch_viterbi_pair_punctured(d_rx, (uint32_t)rx_per_frame, d_ptab, erasure, d_out, ws, n, framebits, blocks, stream);
     if (own) (void)cudaFreeAsync(ws, stream);
     return fail(e, "viterbi kernel launch") ? FEC_ERR_DEVICE : FEC_OK;
 }
@@ -402,12 +421,17 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
 
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
     const size_t in_row = punct ? rx_per_frame : nsym * (is_u32 ? 4 : 1);
+    const size_t idx_bytes = nsym * sizeof(int32_t), ptab_bytes = ((size_t)framebits + 6) / 2 * 16;
+    std::vector<uint32_t> ptab;
     if (punct) {
-        // the table goes up on slot 0's stream; the other slots wait for the event (idx outlives the call's final
-        // synchronise, so the pageable source is safe)
-        if (!grow(&g_pipe.d_idx, &g_pipe.idx_cap, nsym * sizeof(int32_t)) ||
-            fail(cudaMemcpyAsync(g_pipe.d_idx, idx.data(), nsym * sizeof(int32_t), cudaMemcpyHostToDevice, g_pipe.slot[0].stream),
-                 "H2D index table") ||
+        // both table forms go up on slot 0's stream; the other slots wait for the event (the vectors outlive the
+        // call's final synchronise, so the pageable sources are safe)
+        ptab.resize(ptab_bytes / 4);
+        punct_table(framebits, keep, ptab.data());
+        if (!grow(&g_pipe.d_idx, &g_pipe.idx_cap, idx_bytes + ptab_bytes) ||
+            fail(cudaMemcpyAsync(g_pipe.d_idx, idx.data(), idx_bytes, cudaMemcpyHostToDevice, g_pipe.slot[0].stream), "H2D index table") ||
+            fail(cudaMemcpyAsync((uint8_t*)g_pipe.d_idx + idx_bytes, ptab.data(), ptab_bytes, cudaMemcpyHostToDevice, g_pipe.slot[0].stream),
+                 "H2D puncturing table") ||
             fail(cudaEventRecord(g_pipe.idx_ready, g_pipe.slot[0].stream), "cudaEventRecord"))
             return FEC_ERR_DEVICE;
         for (int k = 1; k < kPipe; k++)
@@ -473,6 +497,18 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
             if (in_row && fail(cudaMemcpyAsync(s.d_aux, src, m * in_row, cudaMemcpyHostToDevice, s.stream), "H2D")) {
                 rc = FEC_ERR_DEVICE;
                 break;
+            }
+            if (uses_pair_kernel(m)) {
+                // the throughput kernel expands the rows in its symbol fetch (d_aux carries kPunctSlackBytes of slack)
+                rc = vit_device_punctured(st, framebits, (const uint8_t*)s.d_aux, rx_per_frame, (const uint8_t*)g_pipe.d_idx + idx_bytes,
+                                          erasure, m, (uint8_t*)s.d_out, s.stream, s.d_scratch, s.scratch_cap);
+                if (rc != FEC_OK) break;
+                if (fail(cudaMemcpyAsync(out + done * nout, s.d_out, m * nout, cudaMemcpyDeviceToHost, s.stream), "D2H")) {
+                    rc = FEC_ERR_DEVICE;
+                    break;
+                }
+                done += m;
+                continue;
             }
             if (fail(launch_depuncture((const uint8_t*)s.d_aux, rx_per_frame, (const int32_t*)g_pipe.d_idx, framebits, erasure,
                                        (uint8_t*)s.d_in, m, st->num_sms, s.stream),
@@ -1055,7 +1091,31 @@ int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint
     DeviceState* st = device_state();
     if (!st) return FEC_ERR_DEVICE;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t nsym = 4 * ((size_t)framebits + 6);
+    const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
+    if (uses_pair_kernel(n)) {
+        // Fused path: the throughput kernel expands the rows in its symbol fetch.  Its fetch may touch up to
+        // kPunctSlackBytes past a row, which for every row but the last one is simply the next row; the last frame
+        // is therefore decoded from a padded copy of its row (n - 1 frames in place + 1 frame, two launches).
+        const size_t ptab_bytes = ((size_t)framebits + 6) / 2 * 16, last_bytes = rx_per_frame + kPunctSlackBytes;
+        std::vector<uint32_t> ptab(ptab_bytes / 4);
+        punct_table(framebits, keep, ptab.data());
+        void* d_tmp = nullptr;  // [table][padded last row]
+        if (fail(cudaMallocAsync(&d_tmp, ptab_bytes + last_bytes, s), "cudaMallocAsync(puncturing table)")) return FEC_ERR_DEVICE;
+        uint8_t* d_last = (uint8_t*)d_tmp + ptab_bytes;
+        // ptab is pageable: cudaMemcpyAsync returns once it has been staged, so the vector may die with this call
+        int rc = (fail(cudaMemcpyAsync(d_tmp, ptab.data(), ptab_bytes, cudaMemcpyHostToDevice, s), "H2D puncturing table") ||
+                  fail(cudaMemsetAsync(d_last, 0, last_bytes, s), "cudaMemsetAsync") ||
+                  (rx_per_frame && fail(cudaMemcpyAsync(d_last, d_rx + (n - 1) * rx_per_frame, rx_per_frame, cudaMemcpyDeviceToDevice, s),
+                                        "D2D last row")))
+                     ? FEC_ERR_DEVICE
+                     : FEC_OK;
+        if (rc == FEC_OK && n > 1)
+            rc = vit_device_punctured(st, framebits, d_rx, rx_per_frame, d_tmp, erasure, n - 1, d_out, s, nullptr, 0);
+        if (rc == FEC_OK)
+            rc = vit_device_punctured(st, framebits, d_last, rx_per_frame, d_tmp, erasure, 1, d_out + (n - 1) * nout, s, nullptr, 0);
+        (void)cudaFreeAsync(d_tmp, s);
+        return rc;
+    }
     void *d_idx = nullptr, *d_syms = nullptr;
     if (fail(cudaMallocAsync(&d_idx, nsym * sizeof(int32_t), s), "cudaMallocAsync(index table)")) return FEC_ERR_DEVICE;
     if (fail(cudaMallocAsync(&d_syms, nsym * n, s), "cudaMallocAsync(expanded symbols)")) {

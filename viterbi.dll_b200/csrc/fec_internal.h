@@ -38,6 +38,11 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
 // done_flag (optional, host-mapped): set to 1 by the kernel once its output is visible to the host
 cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
                                 int num_sms, cudaStream_t stream, uint32_t* done_flag = nullptr);
+constexpr size_t kPunctSlackBytes = 16;  // readable bytes the fused depuncturing fetch may touch past the last row
+cudaError_t launch_viterbi_pair_punctured(const uint8_t* d_rx, uint32_t rx_per_frame, const void* d_ptab, uint32_t erasure,
+                                          uint8_t* d_out, void* d_scratch, unsigned long long nframes, uint32_t framebits,
+                                          int grid_blocks, cudaStream_t stream);
+void punct_table(uint32_t framebits, const uint8_t* keep, uint32_t* table);  // (F+6)/2 entries of 4 words
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
                               uint32_t erasure, uint8_t* d_syms, size_t nframes, int num_sms, cudaStream_t stream);
 cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t nsymbols, int num_sms,

@@ -134,12 +134,22 @@ __device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_
 // 64g+L and 64g+32+L).  The grid is persistent (as many warps as fit on the device) and groups are
 // handed out dynamically through a ticket counter so that uneven progress does not leave SM
 // sub-partitions idle at the tail.  scratch: [ticket counter, 256 B][per warp: steps x 32 uint4].
-template <bool kWordStores>
+//
+// kPunct: the depuncturing front end fused into the symbol fetch.  `syms` then holds only
+// the transmitted soft symbols, rx_per_frame bytes per frame, and ptab one entry per loop iteration (two trellis
+// steps = eight mother-code symbols): .x = offset of the iteration's first transmitted symbol inside a row, .y =
+// 8 x (transmitted symbols among the first four), .z = two byte-permute selectors that spread the run over the
+// two step words and put the erasure byte everywhere else.  A thread reads the three aligned words that hold its
+// run of at most eight bytes (rows are dense, so a row starts at any byte), funnel-shifts them into place and
+// expands: ~11 instructions per frame and iteration instead of a separate pass that writes and re-reads the
+// expanded 4(F+6) bytes per frame.  The rows must be followed by 16 readable bytes (the launcher sees to that).
+template <bool kWordStores, bool kPunct>
 __global__ void __launch_bounds__(kVitThreads, kVitMinBlocks)
 viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
-                    unsigned long long nframes, uint32_t framebits) {
+                    unsigned long long nframes, uint32_t framebits, const uint4* __restrict__ ptab, uint32_t rx_per_frame,
+                    uint32_t erasure_word) {
     const uint32_t steps = framebits + 6;  // framebits is even: 2 * ((F + 6) / 2) == F + 6
-    const size_t rowbytes = (size_t)4 * steps, outbytes = (framebits + 7) / 8;
+    const size_t rowbytes = kPunct ? (size_t)rx_per_frame : (size_t)4 * steps, outbytes = (framebits + 7) / 8;
     const uint32_t lane = threadIdx.x & 31u;
     const unsigned long long warp = blockIdx.x, nwarps = gridDim.x;
     const unsigned long long ngroups = (nframes + 63) / 64;
@@ -150,8 +160,24 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
     while (g < ngroups) {
         const unsigned long long fA = g * 64 + lane, fB = fA + 32;
         const bool liveA = fA < nframes, liveB = fB < nframes;
-        const uint2* rowA = reinterpret_cast<const uint2*>(syms + (liveA ? fA : nframes - 1) * rowbytes);
-        const uint2* rowB = reinterpret_cast<const uint2*>(syms + (liveB ? fB : nframes - 1) * rowbytes);
+        const uint8_t* rawA = syms + (liveA ? fA : nframes - 1) * rowbytes;
+        const uint8_t* rawB = syms + (liveB ? fB : nframes - 1) * rowbytes;
+        const uint2* rowA = reinterpret_cast<const uint2*>(rawA);
+        const uint2* rowB = reinterpret_cast<const uint2*>(rawB);
+        // kPunct: the row's aligned base and its misalignment (0..3)
+        const uint32_t misA = (uint32_t)(reinterpret_cast<uintptr_t>(rawA) & 3), misB = (uint32_t)(reinterpret_cast<uintptr_t>(rawB) & 3);
+        const uint8_t* alA = rawA - misA;
+        const uint8_t* alB = rawB - misB;
+        auto fetch_run = [](const uint8_t* al, uint32_t mis, uint32_t off, uint32_t (&w)[3]) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(al + ((mis + off) & ~3u));
+            w[0] = __ldg(p), w[1] = __ldg(p + 1), w[2] = __ldg(p + 2);
+        };
+        auto expand = [erasure_word](const uint32_t (&w)[3], uint32_t mis, const uint4 e) {
+            const uint32_t sh = ((mis + e.x) & 3u) * 8u;
+            const uint32_t lo = __funnelshift_r(w[0], w[1], sh), hi = __funnelshift_r(w[1], w[2], sh);  // the run, byte 0 first
+            const uint32_t q = __funnelshift_rc(lo, hi, e.y);  // ... from the second step's first transmitted symbol on
+            return make_uint2(__byte_perm(lo, erasure_word, e.z & 0xFFFFu), __byte_perm(q, erasure_word, e.z >> 16));
+        };
 
         uint32_t X[64], Y[64];
         X[0] = 0u;  // Locals256: start state 0 has metric 0, all others 63 (deconvolve.cpp:130-132)
@@ -168,36 +194,43 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
         // and save ~30 moves per step, but it overflows the instruction cache once warps are in
         // different phases: measured 94 vs 118 Gbit/s on the MSC batch.)
         uint32_t neg = 0u;
-        uint2 a0 = __ldg(rowA), b0 = __ldg(rowB);  // steps >= 8: the first pairs always exist
-#if VIT_SYM_PREFETCH == 2
-        uint2 a1 = __ldg(rowA + 1), b1 = __ldg(rowB + 1);
-#endif
+        uint2 a0, b0;
+        if (kPunct) {
+            const uint4 e = __ldg(ptab);
+            uint32_t wa[3], wb[3];
+            fetch_run(alA, misA, e.x, wa);
+            fetch_run(alB, misB, e.x, wb);
+            a0 = expand(wa, misA, e), b0 = expand(wb, misB, e);
+        } else {
+            a0 = __ldg(rowA), b0 = __ldg(rowB);  // steps >= 8: the first pairs always exist
+        }
         const uint32_t last_pair = steps / 2 - 1;
         for (uint32_t t = 0; t < steps; t += 2) {
-#if VIT_SYM_PREFETCH == 2
-            uint2 a2 = a1, b2 = b1;
-            if (t + 4 < steps) a2 = __ldg(rowA + (t >> 1) + 2), b2 = __ldg(rowB + (t >> 1) + 2);
-#else
             uint2 na0 = a0, nb0 = b0;
-            if (t + 2 < steps) na0 = __ldg(rowA + (t >> 1) + 1), nb0 = __ldg(rowB + (t >> 1) + 1);
-#endif
-#if VIT_SYM_PREFETCH == 1
-            {
+            uint4 en = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t wa[3] = {0u, 0u, 0u}, wb[3] = {0u, 0u, 0u};
+            if (kPunct) {
+                if (t + 2 < steps) {
+                    en = __ldg(ptab + (t >> 1) + 1);
+                    fetch_run(alA, misA, en.x, wa);
+                    fetch_run(alB, misB, en.x, wb);
+                    // the rows advance by at most 8 bytes per iteration: pull the line ~8 iterations ahead into L1
+                    const uint32_t ahead = min(en.x + 64u, rx_per_frame - 1u);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rawA + ahead));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rawB + ahead));
+                }
+            } else {
+                if (t + 2 < steps) na0 = __ldg(rowA + (t >> 1) + 1), nb0 = __ldg(rowB + (t >> 1) + 1);
                 const uint32_t ahead = min((t >> 1) + kSymPrefetchPairs, last_pair);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(rowA + ahead));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(rowB + ahead));
             }
-#endif
             dec[(size_t)(t + 0) * 32] = acs_step<true>(X, Y, a0.x, b0.x, neg);
             dec[(size_t)(t + 1) * 32] = acs_step<false>(Y, X, a0.y, b0.y, 0u);
             neg = renorm_addend(X[0]);
-#if VIT_SYM_PREFETCH == 2
-            a0 = a1, b0 = b1, a1 = a2, b1 = b2;
-#else
+            if (kPunct && t + 2 < steps) na0 = expand(wa, misA, en), nb0 = expand(wb, misB, en);
             a0 = na0, b0 = nb0;
-#endif
         }
-        (void)last_pair;
         traceback<kWordStores>(dec, lane, framebits, out + fA * outbytes, out + fB * outbytes, liveA, liveB);
 
         unsigned long long next = 0;
@@ -264,13 +297,50 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
     if (e != cudaSuccess) return e;
     // 32-bit output stores need F % 32 == 0 (whole words per row) and a 4-byte aligned d_out
     if (framebits % 32 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0)
-        viterbi_pair_kernel<true><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                            framebits);
+        viterbi_pair_kernel<true, false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
+                                                                                   framebits, nullptr, 0u, 0u);
     else
-        viterbi_pair_kernel<false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                             framebits);
+        viterbi_pair_kernel<false, false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
+                                                                                    framebits, nullptr, 0u, 0u);
     count_launch();
     return cudaGetLastError();
+}
+
+// Punctured input decoded in one pass (kPunct).  d_rx: nframes dense rows of rx_per_frame transmitted symbols,
+// followed by at least kPunctSlackBytes readable bytes; d_ptab: punct_table() on the device.
+cudaError_t launch_viterbi_pair_punctured(const uint8_t* d_rx, uint32_t rx_per_frame, const void* d_ptab, uint32_t erasure,
+                                          uint8_t* d_out, void* d_scratch, unsigned long long nframes, uint32_t framebits,
+                                          int grid_blocks, cudaStream_t stream) {
+    if (nframes == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, kVitScratchHeader, stream);
+    if (e != cudaSuccess) return e;
+    const uint32_t ew = (erasure & 0xFFu) * 0x01010101u;
+    if (framebits % 32 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0)
+        viterbi_pair_kernel<true, true><<<grid_blocks, kVitThreads, 0, stream>>>(d_rx, d_out, (uint8_t*)d_scratch, nframes, framebits,
+                                                                                  (const uint4*)d_ptab, rx_per_frame, ew);
+    else
+        viterbi_pair_kernel<false, true><<<grid_blocks, kVitThreads, 0, stream>>>(d_rx, d_out, (uint8_t*)d_scratch, nframes, framebits,
+                                                                                   (const uint4*)d_ptab, rx_per_frame, ew);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// keep[4*(F+6)] (non-zero = transmitted) -> the per-iteration table of the kPunct kernel: (F+6)/2 entries of 4 words
+void punct_table(uint32_t framebits, const uint8_t* keep, uint32_t* table) {
+    const uint32_t iters = (framebits + 6) / 2;
+    uint32_t off = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        const uint8_t* k = keep + 8 * (size_t)it;
+        uint32_t sel[2] = {0u, 0u}, c[2] = {0u, 0u};
+        for (int w = 0; w < 2; w++)
+            for (int j = 0; j < 4; j++)  // selector nibble: byte c of the (shifted) run, or 4 = byte 0 of the erasure word
+                sel[w] |= (k[4 * w + j] ? c[w]++ : 4u) << (4 * j);
+        table[4 * it + 0] = off;
+        table[4 * it + 1] = 8u * c[0];
+        table[4 * it + 2] = sel[0] | (sel[1] << 16);
+        table[4 * it + 3] = 0u;
+        off += c[0] + c[1];
+    }
 }
 
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kVitWarpThreads) viterbi_warp_kernel(const uin
                                                                          unsigned long long nframes, uint32_t framebits,
                                                                          uint32_t* done_flag) {
     extern __shared__ __align__(16) uint8_t wsmem[];
-    const uint32_t steps = framebits + 6, tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t steps = framebits + 6, tid = threadIdx.x, lane = tid & 31u, nthreads = blockDim.x;  // 32 or 128
     uint32_t* s_sym = reinterpret_cast<uint32_t*>(wsmem);  // [steps + 2] 4 symbols per step (+ a readable pad word, never used); reused by the traceback
     uint2* s_dec = reinterpret_cast<uint2*>(wsmem + 4 * (size_t)(steps + 2));  // [steps] {even, odd} ballots
     const size_t outbytes = (framebits + 7) / 8;
@@ -174,14 +174,14 @@ __global__ void __launch_bounds__(kVitWarpThreads) viterbi_warp_kernel(const uin
         __syncthreads();
         {   // stage the frame: 8-byte loads, eight in flight per thread (over PCIe each round trip costs ~1.5 us)
             const uint2* row = reinterpret_cast<const uint2*>(syms + f * 4 * (size_t)steps);
-            for (uint32_t i0 = tid; i0 < steps / 2; i0 += kVitWarpThreads * 8) {
+            for (uint32_t i0 = tid; i0 < steps / 2; i0 += nthreads * 8) {
                 uint2 v[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (i0 + kVitWarpThreads * u < steps / 2) v[u] = __ldg(row + i0 + kVitWarpThreads * u);
+                    if (i0 + nthreads * u < steps / 2) v[u] = __ldg(row + i0 + nthreads * u);
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (i0 + kVitWarpThreads * u < steps / 2) reinterpret_cast<uint2*>(s_sym)[i0 + kVitWarpThreads * u] = v[u];
+                    if (i0 + nthreads * u < steps / 2) reinterpret_cast<uint2*>(s_sym)[i0 + nthreads * u] = v[u];
             }
         }
         __syncthreads();
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kVitWarpThreads) viterbi_warp_kernel(const uin
         __syncthreads();
         // rotate the decision words left by the lane bit their step's preceding exchange crossed, (5 - t % 5) % 5,
         // so that the traceback's rotate-right by its lane number drops the decision onto that lane bit
-        for (uint32_t tt = 6 + tid; tt < steps; tt += kVitWarpThreads) {
+        for (uint32_t tt = 6 + tid; tt < steps; tt += nthreads) {
             const uint32_t pb = (5u - tt % 5u) % 5u;
             const uint2 d = s_dec[tt];
             s_dec[tt] = make_uint2(__funnelshift_l(d.x, d.x, pb), __funnelshift_l(d.y, d.y, pb));
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kVitWarpThreads) viterbi_warp_kernel(const uin
         bool walked = false;
         if (framebits > 0) {
             // segment length: odd, so that the threads' 8-byte reads / 4-byte writes fall into distinct banks
-            const uint32_t seg = ((framebits + kVitWarpThreads - 1) / kVitWarpThreads) | 1u;
+            const uint32_t seg = ((framebits + nthreads - 1) / nthreads) | 1u;
             const uint32_t lo = 6 + tid * seg, hi = min(lo + seg, steps);  // this thread's steps [lo, hi)
             uint32_t st_in = 0, st_out = 0;
             if (lo < steps) {
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kVitWarpThreads) viterbi_warp_kernel(const uin
         __syncthreads();
         // decoded bit t = the decision consumed at step t + 6 = bit (5 - (t+6) % 5) % 5 of its rotated word;
         // output byte n holds bits 8n .. 8n+7, MSB first (missing bits of a ragged last byte stay 0)
-        for (uint32_t n = tid; n < outbytes; n += kVitWarpThreads) {
+        for (uint32_t n = tid; n < outbytes; n += nthreads) {
             uint32_t v = 0;
 #pragma unroll
             for (uint32_t j = 0; j < 8; j++) {
@@ -343,9 +343,13 @@ cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned 
                                 int num_sms, cudaStream_t stream, uint32_t* done_flag) {
     if (nframes == 0) return cudaSuccess;
     const size_t smem = viterbi_warp_smem_bytes(framebits);
-    const unsigned long long cap = (unsigned long long)num_sms * 16;
+    // Latency shape (a few frames): four warps per block, so that staging, the speculative traceback and the output
+    // pass are spread wide.  Throughput shape (more frames than two per SM): one warp per block -- only warp 0 runs the
+    // trellis, and a 32-thread block lets four times as many frames be resident per SM.
+    const unsigned threads = nframes <= (unsigned long long)num_sms * 2 ? kVitWarpThreads : 32u;
+    const unsigned long long cap = (unsigned long long)num_sms * 32;
     const unsigned grid = (unsigned)(nframes < cap ? nframes : cap);
-    viterbi_warp_kernel<<<grid, kVitWarpThreads, smem, stream>>>(d_syms, d_out, nframes, framebits, done_flag);
+    viterbi_warp_kernel<<<grid, threads, smem, stream>>>(d_syms, d_out, nframes, framebits, done_flag);
     count_launch();
     return cudaGetLastError();
 }
