@@ -295,6 +295,16 @@ def run_b200(args):
     chk_threads = max(1, cores // world)  # every rank checks its own slice at the same time
     parity = {"frames_checked": 0, "superframes_checked": 0, "mismatches": 0}
 
+    if args.only_configs4:  # development aid: just the strong-scaling chain (A/B of gather modes at N = 2..8)
+        c4 = run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, barrier, reduce_ranks)
+        bad = int(reduce_ranks(float(parity["mismatches"]), "sum"))
+        if rank == 0:
+            print(json.dumps({"only": "configs4", "n_gpus": world, "parity_mismatches": bad, "configs4": c4}))
+        if world > 1:
+            barrier()
+            dist.destroy_process_group()
+        return 1 if bad else 0
+
     n, f = args.frames, args.framebits
     steps_per_frame, nsym, nout = f + 6, 4 * (f + 6), (f + 7) // 8
     syms, bits = dabgen.make_frames_torch(n, f, args.ebn0, seed=1234 + rank, device=dev, want_bits=(f % 8 == 0))
@@ -730,9 +740,33 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     gen_s = time.perf_counter() - t0
     allout = torch.full((rounds, world, chunk_sf, 110 * s), 0xEE, dtype=torch.uint8, device=dev)
     allret = torch.full((rounds, world, chunk_sf), -7, dtype=torch.int32, device=dev)
-    comp = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    # How every rank gets every rank's results (the gather of SURVEY 8e), inside the timed region:
+    #   "peer": the RS kernel of the producing rank stores each result tile into every rank's result array itself,
+    #           over NVLink, through CUDA IPC mappings of the peers' arrays (the *_bcast entry points) -- no
+    #           collective, nothing left to do when the kernel ends;
+    #   "nccl": an all_gather_into_tensor per round on a high-priority stream, overlapped with the next round.
+    mode = os.environ.get("BENCH_C4_GATHER", "peer") if world > 1 else "none"
+    peers_out = peers_ret = None
+    if mode == "peer":
+        try:
+            from viterbi_dll_b200 import sharding
+
+            peers_out = sharding.share_with_peers(allout, world, rank)
+            peers_ret = sharding.share_with_peers(allret, world, rank)
+            if vb.lib.fec_enable_peer_access() != 0:
+                raise RuntimeError(vb.lib.fec_last_error())
+        except Exception as e:  # no IPC / no peer access on this box: fall back to the collective
+            mode, peers_out, peers_ret = "nccl (peer mapping failed: %r)" % (e,), None, None
+    others = [r for r in range(world) if r != rank]
+    # two alternating compute streams only when a round is a fraction of the resident set and no collective kernel has
+    # to find room between them: whole-pass rounds (N <= 2) lose nothing to the tail and run ~5 % faster back to back on
+    # one stream (measured, N = 1), and with two streams the next round's blocks fill every slot the previous round
+    # frees, which starves the large blocks of an NCCL kernel until that grid is exhausted (measured, N = 8)
+    nstreams = int(os.environ.get("BENCH_C4_STREAMS", "2" if (chunks_resident > 1 and not mode.startswith("nccl")) else "1"))
+    comp = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
     comm = torch.cuda.Stream(device=dev, priority=-1)
     main = torch.cuda.current_stream()
+    sync_flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def run_job(gather: bool):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -740,9 +774,14 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
         for st in comp + [comm]:
             st.wait_stream(main)
         for j in range(rounds):
-            st = comp[j % 2]
+            st = comp[j % nstreams]
             c = j % chunks_resident
-            vb.dabplus_decode_superframes_device(f, syms[c * chunk_sf * 5:(c + 1) * chunk_sf * 5], allout[j, rank], allret[j, rank], st)
+            sy = syms[c * chunk_sf * 5:(c + 1) * chunk_sf * 5]
+            if gather and mode == "peer":
+                vb.dabplus_decode_superframes_device_bcast(f, sy, allout[j, rank], allret[j, rank], [peers_out[r][j, rank] for r in others],
+                                                           [peers_ret[r][j, rank] for r in others], st)
+                continue
+            vb.dabplus_decode_superframes_device(f, sy, allout[j, rank], allret[j, rank], st)
             if gather and world > 1:
                 done = torch.cuda.Event()
                 done.record(st)
@@ -752,6 +791,8 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
                     dist.all_gather_into_tensor(allret[j].view(-1), allret[j, rank].view(-1))
         for st in comp + [comm]:
             main.wait_stream(st)
+        if gather and mode == "peer":
+            dist.all_reduce(sync_flag)  # on `main`: completes once EVERY rank's kernels (and their peer stores) are done
         end.record(main)
         torch.cuda.synchronize()
         return start.elapsed_time(end)
@@ -777,9 +818,15 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     wrong = int((mine_out[:nres][ok] != pay[ok]).any(dim=1).sum().item())
     accepted = int(ok.sum().item())
     if world > 1:
-        # ranks generate from seed 5000 + 17 * rank: a rank can check a peer's gathered rows only through their
-        # return values being filled in (-7 was the fill)
-        wrong += int((allret == -7).sum().item())
+        # what this rank holds of every peer must be what that peer decoded: compare per-(round, rank) checksums of the
+        # gathered array with the checksums each producer computes over its own slices (a checksum of checksums)
+        barrier()
+        local = torch.stack([torch.stack([torch.stack([a[j, r].sum(dtype=torch.int64) for r in range(world)]) for j in range(rounds)])
+                             for a in (allout, allret)])  # [2, rounds, world] as seen here
+        mine = local[:, :, rank].contiguous()
+        everyone = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(everyone.view(-1), mine.view(-1))
+        wrong += int((everyone.permute(1, 2, 0) != local).sum().item()) + int((allret == -7).sum().item())
     nsl = min(chunk_sf, args.parity_superframes // 8)
     h_syms = syms[: nsl * 5].cpu().numpy()
     dec = chk.deconvolve_batch(f, h_syms, chk_threads)
@@ -798,8 +845,13 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
         "frames_per_s": frames / (ms_gather * 1e-3), "superframes_per_s": job_sf / (ms_gather * 1e-3),
         "viterbi_gbit_per_s": frames * f / (ms_gather * 1e-3) / 1e9,
         "gathered_bytes_per_rank": int(allout.numel() + 4 * allret.numel()) if world > 1 else 0,
-        "gather": "NCCL all_gather_into_tensor per round on a high-priority stream, in place into the full result "
-                  "array, overlapped with the next round; inside ms_total" if world > 1 else "single rank: nothing to gather",
+        "gather": {"peer": "inside ms_total: the RS kernel of each rank stores its result tiles into every rank's result array "
+                           "over NVLink (CUDA IPC peer mappings, dabplus_decode_superframes_device_bcast); a 4-byte all-reduce "
+                           "closes the timed region",
+                   "none": "single rank: nothing to gather"}.get(mode, "inside ms_total: NCCL all_gather_into_tensor per round on a "
+                                                                       "high-priority stream, in place into the full result array, "
+                                                                       "overlapped with the next round (%s)" % mode),
+        "compute_streams": nstreams,
         "gpu_launches_per_rank": launches, "rs_accepted_local": accepted, "rs_accepted_but_wrong_local": wrong,
         "generate_s": gen_s,
     }
@@ -820,6 +872,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the MSC, drop-in, layout and configs[4] side measurements")
     ap.add_argument("--no-configs4", action="store_true", help="skip the 2^24-frame strong-scaling chain")
+    ap.add_argument("--only-configs4", action="store_true", help="run nothing but the configs[4] chain (development aid)")
     ap.add_argument("--msc-frames", type=int, default=262144)
     ap.add_argument("--configs4-frames", type=int, default=1 << 24)
     ap.add_argument("--parity-frames", type=int, default=4096, help="frames per rank compared with the CPU checker")

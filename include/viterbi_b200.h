@@ -160,6 +160,23 @@ int fec_get_devices(int* ordinals, int capacity);
  * device i; streams == NULL or an entry NULL = that device's default stream); the caller synchronises. */
 int fec_allgather_device(const void* const* d_shard, void* const* d_all, size_t bytes_per_shard, void* const* streams);
 
+/* Gather fused into the producing kernel: the same calls as rs_check_superframe_batch_device() /
+ * dabplus_decode_superframes_device(), and every result byte and return value the RS kernel stores into d_out /
+ * d_ret is ALSO stored into ncopies (<= 15) further buffers of the same layout.  With buffers of the peer GPUs
+ * (single process: cudaMalloc + fec_enable_peer_access(); one process per GPU: CUDA IPC mappings) these stores
+ * travel over NVLink while the kernel is still decoding, tile by tile, so every GPU ends up holding every GPU's
+ * results without a collective after the kernel.  Each copy must be congruent to d_out modulo 4 bytes; copies
+ * follow the partial-write rule like d_out itself (pre-fill them the same way).  Visibility on the peers follows
+ * the usual rule: after this stream's work has completed (and the peers have synchronised with it). */
+int rs_check_superframe_batch_device_bcast(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
+                                           int32_t* d_ret, uint8_t* const* d_out_copies, int32_t* const* d_ret_copies,
+                                           int ncopies, void* stream);
+int dabplus_decode_superframes_device_bcast(unsigned int framebits, const uint8_t* d_syms, size_t nsf, uint8_t* d_out,
+                                            int32_t* d_ret, uint8_t* const* d_out_copies, int32_t* const* d_ret_copies,
+                                            int ncopies, void* stream);
+/* cudaDeviceEnablePeerAccess between every pair of the selected devices (single-process hosts). */
+int fec_enable_peer_access(void);
+
 /* ---------------------------------------------------------------------------------------------
  * Device selection and utilities (replace getcpucaps/setupdll per the design brief)
  * ------------------------------------------------------------------------------------------- */
@@ -183,9 +200,10 @@ int fec_memcpy_h2d(void* d_dst, const void* src, size_t bytes);
 int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
 int fec_device_synchronize(void);
 
-/* Viterbi kernel selection: 0 = automatic (warp-per-frame kernel below 4,096 frames per launch, the
- * two-frames-per-thread throughput kernel above), 1 = always the throughput kernel, 2 = always the
- * warp-per-frame kernel.  Both are bit-exact; this exists for tests and measurements. */
+/* Viterbi kernel selection: 0 = automatic (warp-per-frame kernel below 8,192 frames per launch for F <= 1536 and
+ * below 6,144 frames for longer frames -- the measured crossover -- the two-frames-per-thread throughput kernel
+ * above), 1 = always the throughput kernel, 2 = always the warp-per-frame kernel.  Both are bit-exact; this exists
+ * for tests and measurements. */
 #define FEC_VITERBI_AUTO 0
 #define FEC_VITERBI_PAIR 1
 #define FEC_VITERBI_WARP 2

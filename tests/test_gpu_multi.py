@@ -106,6 +106,49 @@ def test_allgather_device_from_one_process(vb):
         assert torch.equal(o.cpu(), want)
 
 
+def test_bcast_stores_results_into_every_copy(vb, checker):
+    """The *_bcast calls: the RS kernel stores its results into extra buffers as well -- on this device and, with
+    peer access, on the others (the gather fused into the producing kernel)."""
+    import torch
+
+    ndev = vb.lib.fec_device_count()
+    vb.set_devices(None)
+    if ndev > 1:
+        assert vb.lib.fec_enable_peer_access() == 0, vb.lib.fec_last_error()
+    torch.cuda.set_device(0)
+    for s, n in ((1, 5001), (5, 3000), (16, 700)):
+        rx, _, _ = dabgen.make_superframes(n, s, seed=70 + s)
+        want_out, want_ret = checker.rs_batch(rx, s, fill=0xEE)
+        d_rx = torch.from_numpy(rx).cuda()
+        out = torch.full((n, 110 * s), 0xEE, dtype=torch.uint8, device="cuda:0")
+        ret = torch.empty((n,), dtype=torch.int32, device="cuda:0")
+        devs = ["cuda:0", "cuda:%d" % (ndev - 1), "cuda:%d" % (1 % ndev)]
+        outs = [torch.full((n, 110 * s), 0xEE, dtype=torch.uint8, device=d) for d in devs]
+        rets = [torch.full((n,), -9, dtype=torch.int32, device=d) for d in devs]
+        vb.rs_check_superframe_batch_device_bcast(d_rx, s, out, ret, outs, rets)
+        torch.cuda.synchronize()
+        for o, r in zip([out] + outs, [ret] + rets):
+            assert np.array_equal(r.cpu().numpy(), want_ret) and np.array_equal(o.cpu().numpy(), want_out), (s, o.device)
+    # the Viterbi -> RS pipeline with copies
+    syms, _, _ = dabgen.make_superframe_frames(900, 768, 2.0, seed=4, max_err=5)
+    dec = checker.deconvolve_batch(768, syms)
+    want_out, want_ret = checker.rs_batch(dec.reshape(900, 480), 4, fill=0xEE)
+    d = torch.from_numpy(syms).cuda()
+    out = torch.full((900, 440), 0xEE, dtype=torch.uint8, device="cuda:0")
+    ret = torch.empty((900,), dtype=torch.int32, device="cuda:0")
+    o2 = torch.full((900, 440), 0xEE, dtype=torch.uint8, device="cuda:%d" % (ndev - 1))
+    r2 = torch.full((900,), -9, dtype=torch.int32, device="cuda:%d" % (ndev - 1))
+    vb.dabplus_decode_superframes_device_bcast(768, d, out, ret, [o2], [r2])
+    torch.cuda.synchronize()
+    for o, r in ((out, ret), (o2, r2)):
+        assert np.array_equal(r.cpu().numpy(), want_ret) and np.array_equal(o.cpu().numpy(), want_out)
+    # argument checks: misaligned copy, too many copies
+    bad = torch.zeros(900 * 440 + 8, dtype=torch.uint8, device="cuda:0")[1:]
+    assert vb.lib.rs_check_superframe_batch_device_bcast(d.data_ptr(), 4, 1, out.data_ptr(), ret.data_ptr(),
+                                                         vb._ptr_array([bad.data_ptr()]), vb._ptr_array([r2.data_ptr()]), 1, None) == vb.FEC_ERR_ARG
+    assert vb.lib.rs_check_superframe_batch_device_bcast(d.data_ptr(), 4, 1, out.data_ptr(), ret.data_ptr(), None, None, 16, None) == vb.FEC_ERR_ARG
+
+
 @pytest.mark.timeout(900)
 @pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
 def test_native_host_decodes_one_batch_on_all_devices(vb, tmp_path):
@@ -157,6 +200,23 @@ def _rank_main(rank, world, port, n, framebits, tmpdir):
     o, r = vb.rs_check_superframe_batch_device(torch.from_numpy(rx[lo2:hi2]).cuda(), 6, o)
     allo = sharding.gather_to_all(o, n // 4, world, rank)
     allr = sharding.gather_to_all(r, n // 4, world, rank)
+    # the same RS results again, gathered by the kernel itself: every rank maps every rank's result arrays (CUDA IPC)
+    # and its RS kernel stores its shard into all of them over NVLink
+    bounds = sharding.all_shards(n // 4, world)
+    full_o = torch.full((n // 4, 660), 0xEE, dtype=torch.uint8, device="cuda")
+    full_r = torch.full((n // 4,), -9, dtype=torch.int32, device="cuda")
+    peers_o = sharding.share_with_peers(full_o, world, rank)
+    peers_r = sharding.share_with_peers(full_r, world, rank)
+    assert vb.lib.fec_enable_peer_access() == 0, vb.lib.fec_last_error()
+    others = [r_ for r_ in range(world) if r_ != rank]
+    vb.rs_check_superframe_batch_device_bcast(torch.from_numpy(rx[lo2:hi2]).cuda(), 6, full_o[lo2:hi2], full_r[lo2:hi2],
+                                              [peers_o[r_][lo2:hi2] for r_ in others], [peers_r[r_][lo2:hi2] for r_ in others])
+    torch.cuda.synchronize()
+    dist.barrier()  # every rank's kernel has finished: all shards have landed everywhere
+    np.save(os.path.join(tmpdir, "bco%d.npy" % rank), full_o.cpu().numpy())
+    np.save(os.path.join(tmpdir, "bcr%d.npy" % rank), full_r.cpu().numpy())
+    dist.barrier()
+    del peers_o, peers_r
     np.save(os.path.join(tmpdir, "vit%d.npy" % rank), allout.cpu().numpy())
     np.save(os.path.join(tmpdir, "rso%d.npy" % rank), allo.cpu().numpy())
     np.save(os.path.join(tmpdir, "rsr%d.npy" % rank), allr.cpu().numpy())
@@ -179,3 +239,5 @@ def test_one_process_per_gpu_shards_and_nccl_gather(vb, checker, tmp_path):
         assert np.array_equal(np.load(tmp_path / ("vit%d.npy" % rank)), want)
         assert np.array_equal(np.load(tmp_path / ("rso%d.npy" % rank)), want_o)
         assert np.array_equal(np.load(tmp_path / ("rsr%d.npy" % rank)), want_r)
+        assert np.array_equal(np.load(tmp_path / ("bco%d.npy" % rank)), want_o)  # gathered by the kernel's own peer stores
+        assert np.array_equal(np.load(tmp_path / ("bcr%d.npy" % rank)), want_r)

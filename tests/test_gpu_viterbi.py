@@ -106,7 +106,8 @@ def test_punctured_input_equals_reference_on_expanded_symbols(vb, kernel, checke
     rng = np.random.default_rng(framebits + n)
     sym, _ = dabgen.make_frames(n, framebits, ebn0, seed=framebits + 3 * n)
     patterns = [dabgen.fic_puncture_pattern()] if framebits == 768 else []
-    patterns.append(dabgen.puncture_pattern(framebits, [(framebits // 32, 8)]))          # rate 1/2 everywhere
+    if framebits % 32 == 0:
+        patterns.append(dabgen.puncture_pattern(framebits, [(framebits // 32, 8)]))      # rate 1/2 everywhere
     patterns.append((rng.random(4 * (framebits + 6)) < 0.6).astype(np.uint8))           # arbitrary pattern
     patterns.append(np.ones(4 * (framebits + 6), np.uint8))                             # nothing punctured
     sparse = (rng.random(4 * (framebits + 6)) < 0.12).astype(np.uint8)                  # whole steps without a symbol,

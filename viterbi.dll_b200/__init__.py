@@ -55,6 +55,9 @@ _SIGNATURES = {
     "fec_get_devices": (ctypes.c_int, [_vp, ctypes.c_int]),
     "fec_allgather_device": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
     "fec_set_thread_device": (ctypes.c_int, [ctypes.c_int]),
+    "rs_check_superframe_batch_device_bcast": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
+    "dabplus_decode_superframes_device_bcast": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
+    "fec_enable_peer_access": (ctypes.c_int, []),
     "fec_device_count": (ctypes.c_int, []),
     "fec_set_device": (ctypes.c_int, [ctypes.c_int]),
     "fec_get_device": (ctypes.c_int, []),
@@ -335,6 +338,35 @@ def allgather_device(shards, outs, streams=None) -> None:
     op = (_vp * n)(*[t.data_ptr() for t in outs])
     st = (_vp * n)(*streams)
     _check(lib.fec_allgather_device(sp, op, nbytes, st), "fec_allgather_device")
+
+
+def _ptr_array(ptrs):
+    return (_vp * max(len(ptrs), 1))(*ptrs)
+
+
+def rs_check_superframe_batch_device_bcast(rx, RSDims: int, out, ret, out_copies, ret_copies, stream=None):
+    """Like rs_check_superframe_batch_device, and the results are also stored into `out_copies` / `ret_copies`: lists
+    of CUDA tensors (same shapes as out / ret; typically peer GPUs' buffers) or raw device pointers (ints)."""
+    n = rx.shape[0]
+    oc = [getattr(t, "data_ptr", lambda t=t: t)() for t in out_copies]
+    rc_ = [getattr(t, "data_ptr", lambda t=t: t)() for t in ret_copies]
+    assert len(oc) == len(rc_) and rx.is_contiguous() and out.is_contiguous() and ret.is_contiguous()
+    rc = lib.rs_check_superframe_batch_device_bcast(rx.data_ptr(), RSDims, n, out.data_ptr(), ret.data_ptr(), _ptr_array(oc),
+                                                    _ptr_array(rc_), len(oc), _stream_ptr(stream))
+    _check(rc, "rs_check_superframe_batch_device_bcast")
+    return out, ret
+
+
+def dabplus_decode_superframes_device_bcast(framebits: int, syms, out, ret, out_copies, ret_copies, stream=None):
+    """Like dabplus_decode_superframes_device with extra destinations (see rs_check_superframe_batch_device_bcast)."""
+    nsf = syms.shape[0] // 5
+    oc = [getattr(t, "data_ptr", lambda t=t: t)() for t in out_copies]
+    rc_ = [getattr(t, "data_ptr", lambda t=t: t)() for t in ret_copies]
+    assert len(oc) == len(rc_) and syms.is_contiguous() and out.is_contiguous() and ret.is_contiguous()
+    rc = lib.dabplus_decode_superframes_device_bcast(framebits, syms.data_ptr(), nsf, out.data_ptr(), ret.data_ptr(),
+                                                     _ptr_array(oc), _ptr_array(rc_), len(oc), _stream_ptr(stream))
+    _check(rc, "dabplus_decode_superframes_device_bcast")
+    return out, ret
 
 
 VITERBI_AUTO, VITERBI_PAIR, VITERBI_WARP = 0, 1, 2

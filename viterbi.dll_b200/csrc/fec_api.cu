@@ -288,16 +288,16 @@ size_t rs_chunk_bytes() {
 bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= VITERBI_B200_MAX_FRAMEBITS; }
 
 // Does a launch of n frames go to the two-frames-per-thread throughput kernel (else: warp-per-frame kernel)?
-bool uses_pair_kernel(size_t n) {
+bool uses_pair_kernel(size_t n, unsigned framebits) {
     const int mode = g_vit_kernel.load();
-    return mode == FEC_VITERBI_PAIR || (mode == FEC_VITERBI_AUTO && n >= kVitWarpKernelMaxFrames);
+    return mode == FEC_VITERBI_PAIR || (mode == FEC_VITERBI_AUTO && n >= vit_warp_kernel_max_frames(framebits));
 }
 
 // Enqueue one batch that is already in device memory.  Scratch is stream-ordered.
 int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_t n, uint8_t* d_out,
                cudaStream_t stream, void* scratch, size_t scratch_cap) {
     if (n == 0 || framebits == 0) return FEC_OK;
-    if (!uses_pair_kernel(n))
+    if (!uses_pair_kernel(n, framebits))
         // latency / small-batch path: decisions stay in shared memory
         return fail(launch_viterbi_warp(d_syms, d_out, n, framebits, st->num_sms, stream), "viterbi warp kernel launch")
                    ? FEC_ERR_DEVICE
@@ -315,13 +315,15 @@ int vit_device(DeviceState* st, unsigned framebits, const uint8_t* d_syms, size_
 // Punctured rows that are already in device memory (followed by kPunctSlackBytes readable bytes): the throughput
 // kernel expands them in its symbol fetch.  d_ptab: punct_table() on the device.
 int vit_device_punctured(DeviceState* st, unsigned framebits, const uint8_t* d_rx, size_t rx_per_frame, const void* d_ptab,
-                         unsigned erasure, size_t n, uint8_t* d_out, cudaStream_t stream, void* scratch, size_t scratch_cap) {
+                         unsigned erasure, size_t n, uint8_t* d_out, cudaStream_t stream, void* scratch, size_t scratch_cap,
+                         const uint8_t* d_last_row = nullptr) {
     const int blocks = viterbi_grid_blocks(st->num_sms, n, framebits);
     const size_t need = viterbi_scratch_bytes(blocks, framebits);
     void* ws = scratch;
     const bool own = (ws == nullptr) || scratch_cap < need;
     if (own && fail(cudaMallocAsync(&ws, need, stream), "cudaMallocAsync(scratch)")) return FEC_ERR_DEVICE;
-    cudaError_t e = launch_viterbi_pair_punctured(d_rx, (uint32_t)rx_per_frame, d_ptab, erasure, d_out, ws, n, framebits, blocks, stream);
+    cudaError_t e = launch_viterbi_pair_punctured(d_rx, (uint32_t)rx_per_frame, d_ptab, erasure, d_out, ws, n, framebits, blocks, stream,
+                                                  d_last_row);
     if (own) (void)cudaFreeAsync(ws, stream);
     return fail(e, "viterbi kernel launch") ? FEC_ERR_DEVICE : FEC_OK;
 }
@@ -464,7 +466,7 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
         // pinned memory is mapped into the device's address space, the kernel stages the symbols into shared
         // memory itself, writes the decoded bytes back through the mapping and raises a completion flag behind
         // them, so the call is one (graph) launch and one poll -- no copy operations, no synchronise.
-        if (!punct && n < kVitWarpKernelMaxFrames && g_vit_kernel.load() != FEC_VITERBI_PAIR) {
+        if (!punct && !uses_pair_kernel(n, framebits)) {
             const int rc = dropin_launch(st, framebits, (const uint8_t*)syms, bounce_out,
                                          reinterpret_cast<uint32_t*>(bounce_out + out_pad), n);
             if (rc == FEC_OK) memcpy(user_out, bounce_out, out_bytes);
@@ -498,7 +500,7 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
                 rc = FEC_ERR_DEVICE;
                 break;
             }
-            if (uses_pair_kernel(m)) {
+            if (uses_pair_kernel(m, framebits)) {
                 // the throughput kernel expands the rows in its symbol fetch (d_aux carries kPunctSlackBytes of slack)
                 rc = vit_device_punctured(st, framebits, (const uint8_t*)s.d_aux, rx_per_frame, (const uint8_t*)g_pipe.d_idx + idx_bytes,
                                           erasure, m, (uint8_t*)s.d_out, s.stream, s.d_scratch, s.scratch_cap);
@@ -1092,10 +1094,10 @@ int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint
     if (!st) return FEC_ERR_DEVICE;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
-    if (uses_pair_kernel(n)) {
+    if (uses_pair_kernel(n, framebits)) {
         // Fused path: the throughput kernel expands the rows in its symbol fetch.  Its fetch may touch up to
-        // kPunctSlackBytes past a row, which for every row but the last one is simply the next row; the last frame
-        // is therefore decoded from a padded copy of its row (n - 1 frames in place + 1 frame, two launches).
+        // kPunctSlackBytes past a row, which for every row but the last one is simply the next row; the last row
+        // is read from a padded copy, so nothing is assumed about what follows the caller's buffer.
         const size_t ptab_bytes = ((size_t)framebits + 6) / 2 * 16, last_bytes = rx_per_frame + kPunctSlackBytes;
         std::vector<uint32_t> ptab(ptab_bytes / 4);
         punct_table(framebits, keep, ptab.data());
@@ -1104,15 +1106,12 @@ int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint
         uint8_t* d_last = (uint8_t*)d_tmp + ptab_bytes;
         // ptab is pageable: cudaMemcpyAsync returns once it has been staged, so the vector may die with this call
         int rc = (fail(cudaMemcpyAsync(d_tmp, ptab.data(), ptab_bytes, cudaMemcpyHostToDevice, s), "H2D puncturing table") ||
-                  fail(cudaMemsetAsync(d_last, 0, last_bytes, s), "cudaMemsetAsync") ||
+                  fail(cudaMemsetAsync(d_last + rx_per_frame, 0, kPunctSlackBytes, s), "cudaMemsetAsync") ||
                   (rx_per_frame && fail(cudaMemcpyAsync(d_last, d_rx + (n - 1) * rx_per_frame, rx_per_frame, cudaMemcpyDeviceToDevice, s),
                                         "D2D last row")))
                      ? FEC_ERR_DEVICE
                      : FEC_OK;
-        if (rc == FEC_OK && n > 1)
-            rc = vit_device_punctured(st, framebits, d_rx, rx_per_frame, d_tmp, erasure, n - 1, d_out, s, nullptr, 0);
-        if (rc == FEC_OK)
-            rc = vit_device_punctured(st, framebits, d_last, rx_per_frame, d_tmp, erasure, 1, d_out + (n - 1) * nout, s, nullptr, 0);
+        if (rc == FEC_OK) rc = vit_device_punctured(st, framebits, d_rx, rx_per_frame, d_tmp, erasure, n, d_out, s, nullptr, 0, d_last);
         (void)cudaFreeAsync(d_tmp, s);
         return rc;
     }
@@ -1142,23 +1141,41 @@ int rs_check_superframe_batch(const uint8_t* in, unsigned int RSDims, size_t n, 
     return rc;
 }
 
-int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
-                                     int32_t* d_ret, void* stream) {
+namespace {
+bool copies_ok(const uint8_t* d_out, uint8_t* const* outs, int32_t* const* rets, int ncopies) {
+    if (ncopies < 0 || ncopies > kRsMaxCopies || (ncopies > 0 && (!outs || !rets))) return false;
+    for (int c = 0; c < ncopies; c++)
+        if (!outs[c] || !rets[c] || ((reinterpret_cast<uintptr_t>(outs[c]) ^ reinterpret_cast<uintptr_t>(d_out)) & 3)) return false;
+    return true;
+}
+}  // namespace
+
+int rs_check_superframe_batch_device_bcast(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out, int32_t* d_ret,
+                                           uint8_t* const* d_out_copies, int32_t* const* d_ret_copies, int ncopies, void* stream) {
     if (RSDims == 0 || RSDims > kRsMaxDims) return bad_arg("RSDims must be 1..1024");
+    if (!copies_ok(d_out, d_out_copies, d_ret_copies, ncopies)) return bad_arg("bad copy list (at most 15, non-null, same alignment modulo 4 as d_out)");
     if (n == 0) return FEC_OK;
     if (!d_in || !d_out || !d_ret) return bad_arg("null pointer");
     DeviceState* st = device_state();
     if (!st) return FEC_ERR_DEVICE;
-    return fail(launch_rs_superframes(d_in, d_out, d_ret, nullptr, n, RSDims, st->num_sms, (cudaStream_t)stream), "rs kernel launch")
+    return fail(launch_rs_superframes(d_in, d_out, d_ret, nullptr, n, RSDims, st->num_sms, (cudaStream_t)stream, d_out_copies,
+                                      d_ret_copies, ncopies),
+                "rs kernel launch")
                ? FEC_ERR_DEVICE
                : FEC_OK;
 }
 
+int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, size_t n, uint8_t* d_out,
+                                     int32_t* d_ret, void* stream) {
+    return rs_check_superframe_batch_device_bcast(d_in, RSDims, n, d_out, d_ret, nullptr, nullptr, 0, stream);
+}
+
 // Viterbi -> superframe -> RS on the device.  Five consecutive decoded frames ARE one superframe
 // ([nsf*5][F/8] == [nsf][120*s] with s = F/192), so no regrouping pass is needed between the kernels.
-int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_syms, size_t nsf, uint8_t* d_out,
-                                      int32_t* d_ret, void* stream) {
+int dabplus_decode_superframes_device_bcast(unsigned int framebits, const uint8_t* d_syms, size_t nsf, uint8_t* d_out, int32_t* d_ret,
+                                            uint8_t* const* d_out_copies, int32_t* const* d_ret_copies, int ncopies, void* stream) {
     if (!vit_args_ok(framebits) || framebits == 0 || framebits % 192u) return bad_arg("framebits must be a multiple of 192");
+    if (!copies_ok(d_out, d_out_copies, d_ret_copies, ncopies)) return bad_arg("bad copy list (at most 15, non-null, same alignment modulo 4 as d_out)");
     if (nsf == 0) return FEC_OK;
     if (!d_syms || !d_out || !d_ret) return bad_arg("null pointer");
     if (reinterpret_cast<uintptr_t>(d_syms) & 7) return bad_arg("d_syms must be 8-byte aligned");
@@ -1169,11 +1186,17 @@ int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_s
     void* d_bits = nullptr;
     if (fail(cudaMallocAsync(&d_bits, nsf * 120 * (size_t)rsdims, s), "cudaMallocAsync(decoded frames)")) return FEC_ERR_DEVICE;
     int rc = vit_device(st, framebits, d_syms, nsf * 5, (uint8_t*)d_bits, s, nullptr, 0);
-    if (rc == FEC_OK && fail(launch_rs_superframes((const uint8_t*)d_bits, d_out, d_ret, nullptr, nsf, rsdims, st->num_sms, s),
+    if (rc == FEC_OK && fail(launch_rs_superframes((const uint8_t*)d_bits, d_out, d_ret, nullptr, nsf, rsdims, st->num_sms, s,
+                                                   d_out_copies, d_ret_copies, ncopies),
                              "rs kernel launch"))
         rc = FEC_ERR_DEVICE;
     (void)cudaFreeAsync(d_bits, s);
     return rc;
+}
+
+int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_syms, size_t nsf, uint8_t* d_out,
+                                      int32_t* d_ret, void* stream) {
+    return dabplus_decode_superframes_device_bcast(framebits, d_syms, nsf, d_out, d_ret, nullptr, nullptr, 0, stream);
 }
 
 int dabplus_decode_superframes(unsigned int framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret) {
@@ -1260,6 +1283,34 @@ int fec_set_devices(const int* ordinals, int count) {
     }
     g_pool.devices = devs;
     return FEC_OK;
+}
+
+int fec_enable_peer_access(void) {
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    std::vector<int> devs;
+    if (!selected_devices(devs)) return FEC_ERR_DEVICE;
+    int cur = -1;
+    (void)cudaGetDevice(&cur);
+    int rc = FEC_OK;
+    for (int a : devs)
+        for (int b : devs) {
+            if (a == b) continue;
+            int can = 0;
+            if (fail(cudaDeviceCanAccessPeer(&can, a, b), "cudaDeviceCanAccessPeer") || !can) {
+                if (t_error.empty()) t_error = "no peer access between devices " + std::to_string(a) + " and " + std::to_string(b);
+                rc = FEC_ERR_DEVICE;
+                continue;
+            }
+            if (cudaSetDevice(a) != cudaSuccess) { rc = FEC_ERR_DEVICE; continue; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                fail(e, "cudaDeviceEnablePeerAccess");
+                rc = FEC_ERR_DEVICE;
+            }
+            (void)cudaGetLastError();
+        }
+    if (cur >= 0) (void)cudaSetDevice(cur);
+    return rc;
 }
 
 int fec_get_devices(int* ordinals, int capacity) {

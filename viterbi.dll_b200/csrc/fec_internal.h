@@ -18,13 +18,14 @@ constexpr int kVitThreads = 32;
 constexpr int kVitMinBlocks = VIT_MIN_BLOCKS;
 constexpr size_t kVitScratchHeader = 256;  // ticket counter, keeps the decision area 256-byte aligned
 
-// Batches below this size go to the warp-per-frame kernel (the pair kernel needs 64 frames per warp
-// and ~600 warps to fill the device).  Measured crossover (profiles/kernel_crossover_r01.jsonl):
-// between 4,096 and 8,192 frames at F=768, between 2,048 and 4,096 at F=3072.
-constexpr unsigned long long kVitWarpKernelMaxFrames = 4096;
+// Batches below this size go to the warp-per-frame kernel (the pair kernel needs 64 frames per warp and takes a flat
+// ~0.33 us x (F+6) for anything up to ~37,000 frames; the warp kernel sustains 24 Gbit/s at F=768 and 18.5 Gbit/s at
+// F=3072).  Measured crossover (profiles/kernel_crossover_r02.jsonl): 8,192 frames at F=768, 6,144 at F=3072.
+constexpr unsigned long long vit_warp_kernel_max_frames(uint32_t framebits) { return framebits <= 1536 ? 8192 : 6144; }
 constexpr int kVitWarpThreads = 128;  // warp-per-frame kernel: warp 0 runs the trellis, all four stage / collect
 constexpr int kRsThreads = 128;
 constexpr uint32_t kMaxFramebits = 9216;  // decision array bound of the reference, deconvolve.cpp:127
+constexpr int kRsMaxCopies = 15;           // extra destinations of one RS launch (peers of a 16-GPU box)
 constexpr uint32_t kRsMaxDims = 1024;     // one superframe must fit a shared-memory tile (120 KB)
 
 void count_launch();
@@ -41,7 +42,7 @@ cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned 
 constexpr size_t kPunctSlackBytes = 16;  // readable bytes the fused depuncturing fetch may touch past the last row
 cudaError_t launch_viterbi_pair_punctured(const uint8_t* d_rx, uint32_t rx_per_frame, const void* d_ptab, uint32_t erasure,
                                           uint8_t* d_out, void* d_scratch, unsigned long long nframes, uint32_t framebits,
-                                          int grid_blocks, cudaStream_t stream);
+                                          int grid_blocks, cudaStream_t stream, const uint8_t* d_last_row);
 void punct_table(uint32_t framebits, const uint8_t* keep, uint32_t* table);  // (F+6)/2 entries of 4 words
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
                               uint32_t erasure, uint8_t* d_syms, size_t nframes, int num_sms, cudaStream_t stream);
@@ -54,7 +55,10 @@ cudaError_t rs_upload_tables();
 cudaError_t rs_configure_device();
 // d_orig: nullptr = in-place semantics (d_out already holds the caller's bytes; untouched columns are not written);
 // else every byte of d_out is written, untouched columns copied from d_orig (same layout as d_out).
+// extra_out / extra_ret [nextra <= kRsMaxCopies]: further destinations (e.g. peer buffers) that receive the same
+// stores as d_out / d_ret; their addresses must be congruent to d_out modulo 4.
 cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, const uint8_t* d_orig,
-                                  unsigned long long nsf, uint32_t s, int num_sms, cudaStream_t stream);
+                                  unsigned long long nsf, uint32_t s, int num_sms, cudaStream_t stream,
+                                  uint8_t* const* extra_out = nullptr, int32_t* const* extra_ret = nullptr, int nextra = 0);
 
 }  // namespace fec

@@ -63,6 +63,16 @@ struct DevicePolicy {
 
 }  // namespace
 
+// Extra destinations of a launch: the kernel stores every result byte and return value it produces into each of
+// them as well (same layout as out / ret).  With peer pointers this IS the gather of the result bitstreams
+//  -- done by the producing kernel's own stores over NVLink, tile by tile, instead of by a
+// collective that follows it.
+struct RsCopies {
+    uint8_t* out[kRsMaxCopies];
+    int32_t* ret[kRsMaxCopies];
+    int n;
+};
+
 // One block = `sf_per_block` whole superframes; static shared memory holds the tables (5 KB), dynamic:
 //   [first_fail int x sf_per_block] [sum int x sf_per_block] [tile]
 // 8 blocks (32 warps) per SM: the launch bound holds the kernel to 64 registers.  Left alone the bit-sliced Chien
@@ -74,7 +84,8 @@ struct DevicePolicy {
 #endif
 __global__ void __launch_bounds__(kRsThreads, RS_MIN_BLOCKS)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
-                     const uint8_t* __restrict__ orig, unsigned long long nsf, uint32_t s, uint32_t sf_per_block) {
+                     const uint8_t* __restrict__ orig, unsigned long long nsf, uint32_t s, uint32_t sf_per_block,
+                     const RsCopies copies) {
     extern __shared__ __align__(16) uint8_t smem[];
     int* s_fail = reinterpret_cast<int*>(smem);
     int* s_sum = s_fail + sf_per_block;
@@ -124,7 +135,11 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
         }
         __syncthreads();
         // ---- return values: sum of the per-column counts, or -1 (rschecksf.cpp:80-88) -------------
-        for (uint32_t n = tid; n < nloc; n += blockDim.x) ret[sf0 + n] = (s_fail[n] < (int)s) ? -1 : s_sum[n];
+        for (uint32_t n = tid; n < nloc; n += blockDim.x) {
+            const int32_t r = (s_fail[n] < (int)s) ? -1 : s_sum[n];
+            ret[sf0 + n] = r;
+            for (int c = 0; c < copies.n; c++) copies.ret[c][sf0 + n] = r;
+        }
         // ---- write back the 110*s data bytes; columns >= first failure stay untouched -------------
         uint8_t* dst = out + sf0 * sf_out;
         for (uint32_t n = 0; n < nloc; n++) {
@@ -136,19 +151,34 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                 // source bytes are gathered from two aligned shared-memory words
                 const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3);
                 const uint32_t nhead = head < sf_out ? head : (uint32_t)sf_out;
-                if (tid < nhead) d[tid] = t[tid];
+                const size_t doff = (size_t)(d - out);  // the same bytes go to every extra copy (peer buffers over NVLink)
+                if (tid < nhead) {
+                    d[tid] = t[tid];
+                    for (int c = 0; c < copies.n; c++) copies.out[c][doff + tid] = t[tid];
+                }
                 const size_t nwords = (sf_out - nhead) / 4;
                 const uint32_t toff = (uint32_t)(reinterpret_cast<uintptr_t>(t + nhead) & 3);
                 const uint32_t* tw = reinterpret_cast<const uint32_t*>(t + nhead - toff);
                 const uint32_t sel = 0x3210u + 0x1111u * toff;
-                for (size_t w = tid; w < nwords; w += blockDim.x)
-                    reinterpret_cast<uint32_t*>(d + nhead)[w] = __byte_perm(tw[w], tw[w + 1], sel);
-                for (size_t i = nhead + nwords * 4 + tid; i < sf_out; i += blockDim.x) d[i] = t[i];
+                for (size_t w = tid; w < nwords; w += blockDim.x) {
+                    const uint32_t v = __byte_perm(tw[w], tw[w + 1], sel);
+                    reinterpret_cast<uint32_t*>(d + nhead)[w] = v;
+                    for (int c = 0; c < copies.n; c++) reinterpret_cast<uint32_t*>(copies.out[c] + doff + nhead)[w] = v;
+                }
+                for (size_t i = nhead + nwords * 4 + tid; i < sf_out; i += blockDim.x) {
+                    d[i] = t[i];
+                    for (int c = 0; c < copies.n; c++) copies.out[c][doff + i] = t[i];
+                }
             } else if (orig == nullptr) {
                 // i % s through a multiply-high (s is launch-uniform; exact for i < 2^17, s <= 1024)
-                if (fail > 0)
+                if (fail > 0) {
+                    const size_t doff = (size_t)(d - out);
                     for (uint32_t i = tid; i < (uint32_t)sf_out; i += blockDim.x)
-                        if (i - __umulhi(i, inv_s) * s < fail) d[i] = t[i];
+                        if (i - __umulhi(i, inv_s) * s < fail) {
+                            d[i] = t[i];
+                            for (int c = 0; c < copies.n; c++) copies.out[c][doff + i] = t[i];
+                        }
+                }
             }
         }
         if (orig != nullptr) {
@@ -281,7 +311,8 @@ cudaError_t rs_configure_device() {
 }
 
 cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, const uint8_t* d_orig,
-                                  unsigned long long nsf, uint32_t s, int num_sms, cudaStream_t stream) {
+                                  unsigned long long nsf, uint32_t s, int num_sms, cudaStream_t stream,
+                                  uint8_t* const* extra_out, int32_t* const* extra_ret, int nextra) {
     if (nsf == 0) return cudaSuccess;
     const uint32_t spb = rs_superframes_per_block(s);
     const size_t smem = rs_smem_bytes(s, spb);
@@ -295,7 +326,14 @@ cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* 
     }
     const unsigned long long cap = (unsigned long long)num_sms * (unsigned)per_sm;
     if (nblk > cap) nblk = cap;
-    rs_superframe_kernel<<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, d_orig, nsf, s, spb);
+    RsCopies copies;
+    copies.n = 0;
+    for (int c = 0; c < nextra && c < kRsMaxCopies; c++) {
+        copies.out[copies.n] = extra_out[c];
+        copies.ret[copies.n] = extra_ret[c];
+        copies.n++;
+    }
+    rs_superframe_kernel<<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, d_orig, nsf, s, spb, copies);
     count_launch();
     return cudaGetLastError();
 }

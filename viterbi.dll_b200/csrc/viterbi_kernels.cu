@@ -147,7 +147,7 @@ template <bool kWordStores, bool kPunct>
 __global__ void __launch_bounds__(kVitThreads, kVitMinBlocks)
 viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
                     unsigned long long nframes, uint32_t framebits, const uint4* __restrict__ ptab, uint32_t rx_per_frame,
-                    uint32_t erasure_word) {
+                    uint32_t erasure_word, const uint8_t* __restrict__ last_row) {
     const uint32_t steps = framebits + 6;  // framebits is even: 2 * ((F + 6) / 2) == F + 6
     const size_t rowbytes = kPunct ? (size_t)rx_per_frame : (size_t)4 * steps, outbytes = (framebits + 7) / 8;
     const uint32_t lane = threadIdx.x & 31u;
@@ -160,8 +160,11 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
     while (g < ngroups) {
         const unsigned long long fA = g * 64 + lane, fB = fA + 32;
         const bool liveA = fA < nframes, liveB = fB < nframes;
-        const uint8_t* rawA = syms + (liveA ? fA : nframes - 1) * rowbytes;
-        const uint8_t* rawB = syms + (liveB ? fB : nframes - 1) * rowbytes;
+        // kPunct: the fetch may touch a few bytes past a row, which is the next row except for the very last one:
+        // that row is read from a padded copy when the caller's buffer has no slack (last_row != nullptr)
+        const unsigned long long rA = liveA ? fA : nframes - 1, rB = liveB ? fB : nframes - 1;
+        const uint8_t* rawA = (kPunct && last_row != nullptr && rA == nframes - 1) ? last_row : syms + rA * rowbytes;
+        const uint8_t* rawB = (kPunct && last_row != nullptr && rB == nframes - 1) ? last_row : syms + rB * rowbytes;
         const uint2* rowA = reinterpret_cast<const uint2*>(rawA);
         const uint2* rowB = reinterpret_cast<const uint2*>(rawB);
         // kPunct: the row's aligned base and its misalignment (0..3)
@@ -298,29 +301,30 @@ cudaError_t launch_viterbi_pair(const uint8_t* d_syms, uint8_t* d_out, void* d_s
     // 32-bit output stores need F % 32 == 0 (whole words per row) and a 4-byte aligned d_out
     if (framebits % 32 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0)
         viterbi_pair_kernel<true, false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                                   framebits, nullptr, 0u, 0u);
+                                                                                   framebits, nullptr, 0u, 0u, nullptr);
     else
         viterbi_pair_kernel<false, false><<<grid_blocks, kVitThreads, 0, stream>>>(d_syms, d_out, (uint8_t*)d_scratch, nframes,
-                                                                                    framebits, nullptr, 0u, 0u);
+                                                                                    framebits, nullptr, 0u, 0u, nullptr);
     count_launch();
     return cudaGetLastError();
 }
 
-// Punctured input decoded in one pass (kPunct).  d_rx: nframes dense rows of rx_per_frame transmitted symbols,
-// followed by at least kPunctSlackBytes readable bytes; d_ptab: punct_table() on the device.
+// Punctured input decoded in one pass (kPunct).  d_rx: nframes dense rows of rx_per_frame transmitted symbols;
+// d_ptab: punct_table() on the device; d_last_row: nullptr when d_rx is followed by at least kPunctSlackBytes
+// readable bytes, else a copy of the last row that is.
 cudaError_t launch_viterbi_pair_punctured(const uint8_t* d_rx, uint32_t rx_per_frame, const void* d_ptab, uint32_t erasure,
                                           uint8_t* d_out, void* d_scratch, unsigned long long nframes, uint32_t framebits,
-                                          int grid_blocks, cudaStream_t stream) {
+                                          int grid_blocks, cudaStream_t stream, const uint8_t* d_last_row) {
     if (nframes == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(d_scratch, 0, kVitScratchHeader, stream);
     if (e != cudaSuccess) return e;
     const uint32_t ew = (erasure & 0xFFu) * 0x01010101u;
     if (framebits % 32 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0)
         viterbi_pair_kernel<true, true><<<grid_blocks, kVitThreads, 0, stream>>>(d_rx, d_out, (uint8_t*)d_scratch, nframes, framebits,
-                                                                                  (const uint4*)d_ptab, rx_per_frame, ew);
+                                                                                  (const uint4*)d_ptab, rx_per_frame, ew, d_last_row);
     else
         viterbi_pair_kernel<false, true><<<grid_blocks, kVitThreads, 0, stream>>>(d_rx, d_out, (uint8_t*)d_scratch, nframes, framebits,
-                                                                                   (const uint4*)d_ptab, rx_per_frame, ew);
+                                                                                   (const uint4*)d_ptab, rx_per_frame, ew, d_last_row);
     count_launch();
     return cudaGetLastError();
 }

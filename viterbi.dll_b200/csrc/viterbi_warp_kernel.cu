@@ -42,7 +42,7 @@ namespace fec {
 // The block has four warps: all of them stage the symbols (over PCIe when the input is the caller's pinned bounce
 // buffer: enough loads in flight for one round trip) and collect the output; warp 0 alone runs the trellis.
 // ~25 warp-instructions per trellis step against 6.5 per frame-step for the pair kernel, so it is used where the
-// pair kernel cannot fill the machine: the single-frame drop-in call and batches below kVitWarpKernelMaxFrames.
+// pair kernel cannot fill the machine: the single-frame drop-in call and batches below vit_warp_kernel_max_frames().
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
