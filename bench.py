@@ -738,25 +738,29 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     syms, payload = dabgen.make_superframe_frames_torch(res_sf, f, 4.0, seed=5000 + 17 * rank, device=dev, max_err=3)
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
-    allout = torch.full((rounds, world, chunk_sf, 110 * s), 0xEE, dtype=torch.uint8, device=dev)
-    allret = torch.full((rounds, world, chunk_sf), -7, dtype=torch.int32, device=dev)
     # How every rank gets every rank's results (the gather of SURVEY 8e), inside the timed region:
     #   "peer": the RS kernel of the producing rank stores each result tile into every rank's result array itself,
     #           over NVLink, through CUDA IPC mappings of the peers' arrays (the *_bcast entry points) -- no
     #           collective, nothing left to do when the kernel ends;
     #   "nccl": an all_gather_into_tensor per round on a high-priority stream, overlapped with the next round.
     mode = os.environ.get("BENCH_C4_GATHER", "peer") if world > 1 else "none"
-    peers_out = peers_ret = None
+    out_bytes, ret_bytes = rounds * world * chunk_sf * 110 * s, rounds * world * chunk_sf * 4
+    buf_out = buf_ret = None
     if mode == "peer":
         try:
-            from viterbi_dll_b200 import sharding
-
-            peers_out = sharding.share_with_peers(allout, world, rank)
-            peers_ret = sharding.share_with_peers(allret, world, rank)
-            if vb.lib.fec_enable_peer_access() != 0:
-                raise RuntimeError(vb.lib.fec_last_error())
-        except Exception as e:  # no IPC / no peer access on this box: fall back to the collective
-            mode, peers_out, peers_ret = "nccl (peer mapping failed: %r)" % (e,), None, None
+            buf_out = vb.PeerBuffer(out_bytes, world, rank, dev.index)
+            buf_ret = vb.PeerBuffer(ret_bytes, world, rank, dev.index)
+        except Exception as e:  # no IPC / no peer access on this box: fall back to the collective (all ranks fail alike)
+            mode, buf_out, buf_ret = "nccl (peer mapping failed: %r)" % (e,), None, None
+    if buf_out is not None:
+        allout = buf_out.local.view(rounds, world, chunk_sf, 110 * s)
+        allret = buf_ret.local.view(torch.int32).view(rounds, world, chunk_sf)
+        allout.fill_(0xEE)
+        allret.fill_(-7)
+    else:
+        allout = torch.full((rounds, world, chunk_sf, 110 * s), 0xEE, dtype=torch.uint8, device=dev)
+        allret = torch.full((rounds, world, chunk_sf), -7, dtype=torch.int32, device=dev)
+    barrier()  # every rank's arrays are pre-filled before anybody stores into them
     others = [r for r in range(world) if r != rank]
     # two alternating compute streams only when a round is a fraction of the resident set and no collective kernel has
     # to find room between them: whole-pass rounds (N <= 2) lose nothing to the tail and run ~5 % faster back to back on
@@ -778,8 +782,9 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
             c = j % chunks_resident
             sy = syms[c * chunk_sf * 5:(c + 1) * chunk_sf * 5]
             if gather and mode == "peer":
-                vb.dabplus_decode_superframes_device_bcast(f, sy, allout[j, rank], allret[j, rank], [peers_out[r][j, rank] for r in others],
-                                                           [peers_ret[r][j, rank] for r in others], st)
+                vb.dabplus_decode_superframes_device_bcast(f, sy, allout[j, rank], allret[j, rank],
+                                                           [buf_out.peer_ptr(r, allout[j, rank]) for r in others],
+                                                           [buf_ret.peer_ptr(r, allret[j, rank]) for r in others], st)
                 continue
             vb.dabplus_decode_superframes_device(f, sy, allout[j, rank], allret[j, rank], st)
             if gather and world > 1:
@@ -836,6 +841,11 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     parity["mismatches"] += int((c_ret != mine_ret[0, :nsl].cpu().numpy()).sum()) + \
         int((c_out != mine_out[0, :nsl].cpu().numpy()).any(axis=1).sum()) + wrong
     frames = job_sf * 5
+    gathered = int(allout.numel() + 4 * allret.numel()) if world > 1 else 0
+    del mine_out, mine_ret, allout, allret
+    if buf_out is not None:
+        buf_out.close()
+        buf_ret.close()
     return {
         "workload": "BASELINE configs[4]: %d MSC frames (F=3072) -> %d DAB+ superframes (s=16), Viterbi + RS check on "
                     "device, Eb/N0=4 dB, 0-3 byte errors per codeword before the convolutional encoder" % (frames, job_sf),
@@ -844,7 +854,7 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
         "ms_total": ms_gather, "ms_total_without_gather": ms_nogather,
         "frames_per_s": frames / (ms_gather * 1e-3), "superframes_per_s": job_sf / (ms_gather * 1e-3),
         "viterbi_gbit_per_s": frames * f / (ms_gather * 1e-3) / 1e9,
-        "gathered_bytes_per_rank": int(allout.numel() + 4 * allret.numel()) if world > 1 else 0,
+        "gathered_bytes_per_rank": gathered,
         "gather": {"peer": "inside ms_total: the RS kernel of each rank stores its result tiles into every rank's result array "
                            "over NVLink (CUDA IPC peer mappings, dabplus_decode_superframes_device_bcast); a 4-byte all-reduce "
                            "closes the timed region",

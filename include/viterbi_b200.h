@@ -176,6 +176,13 @@ int dabplus_decode_superframes_device_bcast(unsigned int framebits, const uint8_
                                             int ncopies, void* stream);
 /* cudaDeviceEnablePeerAccess between every pair of the selected devices (single-process hosts). */
 int fec_enable_peer_access(void);
+/* One process per GPU: export a buffer from fec_device_alloc() as a 64-byte CUDA IPC handle, map a peer process's
+ * buffer into this process for the calling thread's device (with peer access; returns NULL on failure), unmap it.
+ * The exporter keeps the buffer allocated while peers have it mapped. */
+#define FEC_IPC_HANDLE_BYTES 64
+int fec_ipc_export(const void* d_ptr, unsigned char* handle /* [FEC_IPC_HANDLE_BYTES] */);
+void* fec_ipc_import(const unsigned char* handle);
+int fec_ipc_close(void* d_ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * Device selection and utilities (replace getcpucaps/setupdll per the design brief)

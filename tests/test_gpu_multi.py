@@ -202,21 +202,26 @@ def _rank_main(rank, world, port, n, framebits, tmpdir):
     allr = sharding.gather_to_all(r, n // 4, world, rank)
     # the same RS results again, gathered by the kernel itself: every rank maps every rank's result arrays (CUDA IPC)
     # and its RS kernel stores its shard into all of them over NVLink
-    bounds = sharding.all_shards(n // 4, world)
-    full_o = torch.full((n // 4, 660), 0xEE, dtype=torch.uint8, device="cuda")
-    full_r = torch.full((n // 4,), -9, dtype=torch.int32, device="cuda")
-    peers_o = sharding.share_with_peers(full_o, world, rank)
-    peers_r = sharding.share_with_peers(full_r, world, rank)
-    assert vb.lib.fec_enable_peer_access() == 0, vb.lib.fec_last_error()
+    nsf = n // 4
+    buf_o = vb.PeerBuffer(nsf * 660, world, rank, rank)
+    buf_r = vb.PeerBuffer(nsf * 4, world, rank, rank)
+    full_o = buf_o.local.view(nsf, 660)
+    full_r = buf_r.local.view(torch.int32)
+    full_o.fill_(0xEE)
+    full_r.fill_(-9)
+    torch.cuda.synchronize()
+    dist.barrier()  # every rank's arrays are pre-filled before anybody stores into them
     others = [r_ for r_ in range(world) if r_ != rank]
     vb.rs_check_superframe_batch_device_bcast(torch.from_numpy(rx[lo2:hi2]).cuda(), 6, full_o[lo2:hi2], full_r[lo2:hi2],
-                                              [peers_o[r_][lo2:hi2] for r_ in others], [peers_r[r_][lo2:hi2] for r_ in others])
+                                              [buf_o.peer_ptr(r_, full_o[lo2:hi2]) for r_ in others],
+                                              [buf_r.peer_ptr(r_, full_r[lo2:hi2]) for r_ in others])
     torch.cuda.synchronize()
     dist.barrier()  # every rank's kernel has finished: all shards have landed everywhere
     np.save(os.path.join(tmpdir, "bco%d.npy" % rank), full_o.cpu().numpy())
     np.save(os.path.join(tmpdir, "bcr%d.npy" % rank), full_r.cpu().numpy())
-    dist.barrier()
-    del peers_o, peers_r
+    del full_o, full_r
+    buf_o.close()
+    buf_r.close()
     np.save(os.path.join(tmpdir, "vit%d.npy" % rank), allout.cpu().numpy())
     np.save(os.path.join(tmpdir, "rso%d.npy" % rank), allo.cpu().numpy())
     np.save(os.path.join(tmpdir, "rsr%d.npy" % rank), allr.cpu().numpy())

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "rs_check_superframe_batch_device_bcast": (ctypes.c_int, [_vp, ctypes.c_uint, ctypes.c_size_t, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "dabplus_decode_superframes_device_bcast": (ctypes.c_int, [ctypes.c_uint, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, ctypes.c_int, _vp]),
     "fec_enable_peer_access": (ctypes.c_int, []),
+    "fec_ipc_export": (ctypes.c_int, [_vp, _vp]),
+    "fec_ipc_import": (_vp, [_vp]),
+    "fec_ipc_close": (ctypes.c_int, [_vp]),
     "fec_device_count": (ctypes.c_int, []),
     "fec_set_device": (ctypes.c_int, [ctypes.c_int]),
     "fec_get_device": (ctypes.c_int, []),
@@ -338,6 +341,58 @@ def allgather_device(shards, outs, streams=None) -> None:
     op = (_vp * n)(*[t.data_ptr() for t in outs])
     st = (_vp * n)(*streams)
     _check(lib.fec_allgather_device(sp, op, nbytes, st), "fec_allgather_device")
+
+
+class PeerBuffer:
+    """A device buffer of this rank (fec_device_alloc) that every rank of the node has mapped (CUDA IPC): `local` is
+    a torch uint8 view of this rank's buffer, `base[r]` the address of rank r's buffer in THIS process.  Used with the
+    *_bcast calls: a kernel of this rank stores its results into every rank's buffer over NVLink.  Collective over
+    the default process group: every rank constructs it with the same size, and calls close() together."""
+
+    def __init__(self, nbytes: int, world: int, rank: int, device_index: int):
+        import torch
+        import torch.distributed as dist
+
+        self.nbytes, self.world, self.rank = nbytes, world, rank
+        self.ptr = lib.fec_device_alloc(nbytes)
+        if not self.ptr:
+            raise FecError("fec_device_alloc failed: %s" % (lib.fec_last_error() or b"").decode())
+        handle = (ctypes.c_ubyte * 64)()
+        _check(lib.fec_ipc_export(self.ptr, handle), "fec_ipc_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda:%d" % device_index)
+        allh = torch.empty((world, 64), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh.view(-1), mine)
+        allh = allh.cpu().numpy()
+        self.base = []
+        for r in range(world):
+            if r == rank:
+                self.base.append(self.ptr)
+                continue
+            p = lib.fec_ipc_import((ctypes.c_ubyte * 64)(*allh[r].tolist()))
+            if not p:
+                raise FecError("fec_ipc_import failed: %s" % (lib.fec_last_error() or b"").decode())
+            self.base.append(p)
+
+        class _Arr:  # zero-copy torch view of the raw allocation
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+        self.local = torch.as_tensor(_Arr(), device="cuda:%d" % device_index)
+
+    def peer_ptr(self, r: int, view) -> int:
+        """Address, in rank r's buffer, of the bytes that `view` (a view of self.local) covers here."""
+        return self.base[r] + (view.data_ptr() - self.ptr)
+
+    def close(self):
+        import torch.distributed as dist
+
+        dist.barrier()  # nobody stores into a peer that is about to unmap / free
+        for r, p in enumerate(self.base):
+            if r != self.rank and p:
+                lib.fec_ipc_close(p)
+        dist.barrier()
+        self.local = None
+        lib.fec_device_free(self.ptr)
+        self.base, self.ptr = [], None
 
 
 def _ptr_array(ptrs):

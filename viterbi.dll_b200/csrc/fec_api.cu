@@ -1313,6 +1313,38 @@ int fec_enable_peer_access(void) {
     return rc;
 }
 
+// ---- CUDA IPC: one process per GPU hosts map each other's result buffers, so that the *_bcast kernels can store
+// into them over NVLink.  The import happens with the CALLING thread's device current and lazy peer access, which is
+// what makes the mapping usable from kernels of that device (a mapping opened under the exporting device's ordinal
+// is not, even with peer access enabled afterwards).
+int fec_ipc_export(const void* d_ptr, unsigned char* handle) {
+    if (!d_ptr || !handle) return bad_arg("null pointer");
+    if (!device_state()) return FEC_ERR_DEVICE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == FEC_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    if (fail(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)), "cudaIpcGetMemHandle")) return FEC_ERR_DEVICE;
+    memcpy(handle, &h, sizeof h);
+    return FEC_OK;
+}
+
+void* fec_ipc_import(const unsigned char* handle) {
+    if (!handle) {
+        bad_arg("null pointer");
+        return nullptr;
+    }
+    if (!device_state()) return nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    if (fail(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return nullptr;
+    return p;
+}
+
+int fec_ipc_close(void* d_ptr) {
+    if (!d_ptr) return FEC_OK;
+    return fail(cudaIpcCloseMemHandle(d_ptr), "cudaIpcCloseMemHandle") ? FEC_ERR_DEVICE : FEC_OK;
+}
+
 int fec_get_devices(int* ordinals, int capacity) {
     std::lock_guard<std::mutex> lock(g_pool.mu);
     std::vector<int> devs;

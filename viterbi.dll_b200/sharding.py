@@ -44,17 +44,3 @@ def gather_to_all(local, n_total: int, world: int, rank: int, align: int = 1, gr
     parts = [out[r * width : r * width + (h - l)] for r, (l, h) in enumerate(bounds)]
     return torch.cat(parts, dim=0)
 
-
-def share_with_peers(t, world: int, rank: int, group=None):
-    """One process per GPU: make the CUDA tensor `t` of every rank addressable from every other rank of the node.
-    Returns a list of `world` tensors -- entry r aliases rank r's `t` (CUDA IPC mapping; entry `rank` is `t`
-    itself).  Kernels of this rank may store into the peers' tensors over NVLink once peer access is enabled
-    (fec_enable_peer_access), which is how the *_bcast calls gather results without a collective.  Every rank
-    must keep its own `t` alive while peers use it."""
-    import torch.distributed as dist
-    from torch.multiprocessing.reductions import reduce_tensor
-
-    assert t.is_cuda and t.is_contiguous()
-    objs = [None] * world
-    dist.all_gather_object(objs, reduce_tensor(t), group=group)
-    return [t if r == rank else objs[r][0](*objs[r][1]) for r in range(world)]
