@@ -709,64 +709,78 @@ def run_b200(args):
 
 def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, barrier, reduce_ranks):
     """BASELINE configs[4]: `--configs4-frames` (2^24) MSC frames = 3.36 M DAB+ superframes (s = 16), Viterbi + RS check
-    on the device, STRONG scaling: the job is the same whatever N is.
+    on the device, STRONG scaling: the job is the same whatever N is, and the timed region ends when EVERY rank holds
+    EVERY result (the gather of SURVEY 8e is inside it).
 
-    The job is cut into rounds of `world` chunks; rank r decodes chunk r of every round, so the all-gather of a
-    round lands in natural superframe order.  A rank keeps at most 2^21 frames of symbols (25.8 GB) resident and
-    reuses them round after round (206 GB of symbols do not fit one GPU; every pass streams far more than the
-    126 MB L2, so a repeated pass costs what a fresh one does).  Rounds alternate between two compute streams so
-    that the tail of one round's persistent Viterbi grid is filled by the next round's blocks; the NCCL
-    all-gather of round j (results + return values, in place into the full result array) runs on a third,
-    high-priority stream while round j+1 computes.  The timed region ends when every rank holds every result."""
+    The job is cut into rounds; in every round each rank decodes one contiguous slice, and the slices of a round sit
+    side by side in the result array, so the gather of a round is one contiguous all-gather in natural superframe
+    order.  A round is a whole number of WAVES of the persistent Viterbi grid (148 SMs x 16 warps x 64 frames), so
+    cutting the work into rounds costs nothing at the tail of a launch; a rank's share is cut into at least four
+    rounds, the last one the small remainder, because the gather of the last round is the only one that cannot hide
+    behind decoding.  A rank keeps at most 2^21 frames of symbols (25.8 GB) resident and reuses them (206 GB of
+    symbols do not fit one GPU; a pass streams far more than the 126 MB L2, so a repeated pass costs what a fresh one
+    does).  Gather: NCCL all_gather_into_tensor per round, in place, on a high-priority stream beside ONE compute
+    stream (the collective and the next round then become runnable together and the priority puts the collective's
+    few blocks first; with a second compute stream the next round's blocks refill every slot as it frees and the
+    collective's large blocks starve until that grid is exhausted -- measured at N = 8: 58.2 vs 53.5 ms).
+    BENCH_C4_GATHER=peer uses the fused alternative instead: the RS kernel stores its result tiles into every rank's
+    array itself through CUDA IPC peer mappings (the *_bcast entry points; no collective at all)."""
     import torch
     import torch.distributed as dist
 
     f, s = 3072, 16
+    row = 110 * s
     total_sf = args.configs4_frames // 5
-    res_sf_cap = -(-(1 << 21) // 5)  # 2^21 frames of symbols (25.8 GB) resident per GPU
     my_sf = -(-total_sf // world)
-    # one round = one launch per rank.  Large launches lose the least to the tail of the persistent grid, but the
-    # gather of the LAST round cannot overlap anything, so a rank's share is cut into at least four rounds
-    # (N = 8: four rounds of 2^19 frames; N = 1: eight resident passes of 2^21 frames).
-    passes = -(-my_sf // res_sf_cap)
-    rounds = max(4, passes)
-    chunk_sf = -(-my_sf // rounds)
-    chunks_resident = max(1, min(rounds, res_sf_cap // chunk_sf))
-    res_sf = chunk_sf * chunks_resident
-    job_sf = rounds * world * chunk_sf  # superframes actually decoded (>= total_sf: the last round is padded)
+    wave_sf = (torch.cuda.get_device_properties(dev).multi_processor_count * 16 * 64) // 5  # superframes per wave
+    res_cap = max(wave_sf, ((1 << 21) // 5) // wave_sf * wave_sf)  # resident symbols: whole waves, <= 2^21 frames
+    per_round = max(wave_sf, min(res_cap, (my_sf // 4) // wave_sf * wave_sf))
+    sizes = [per_round] * (my_sf // per_round)
+    if my_sf - sum(sizes) > 0:
+        sizes.append(my_sf - sum(sizes))
+    rounds = len(sizes)
+    offs = [sum(sizes[:j]) for j in range(rounds)]
+    res_sf = min(my_sf, res_cap)
+    job_sf = my_sf * world  # superframes actually decoded (>= total_sf)
+    starts = []  # which resident superframes a round decodes: consecutive slices, wrapping when the set is exhausted
+    cur = 0
+    for sz in sizes:
+        if cur + sz > res_sf:
+            cur = 0
+        starts.append(cur)
+        cur += sz
     t0 = time.perf_counter()
     syms, payload = dabgen.make_superframe_frames_torch(res_sf, f, 4.0, seed=5000 + 17 * rank, device=dev, max_err=3)
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
-    # How every rank gets every rank's results (the gather of SURVEY 8e), inside the timed region:
-    #   "peer": the RS kernel of the producing rank stores each result tile into every rank's result array itself,
-    #           over NVLink, through CUDA IPC mappings of the peers' arrays (the *_bcast entry points) -- no
-    #           collective, nothing left to do when the kernel ends;
-    #   "nccl": an all_gather_into_tensor per round on a high-priority stream, overlapped with the next round.
-    mode = os.environ.get("BENCH_C4_GATHER", "peer") if world > 1 else "none"
-    out_bytes, ret_bytes = rounds * world * chunk_sf * 110 * s, rounds * world * chunk_sf * 4
+
+    mode = os.environ.get("BENCH_C4_GATHER", "nccl") if world > 1 else "none"
     buf_out = buf_ret = None
     if mode == "peer":
         try:
-            buf_out = vb.PeerBuffer(out_bytes, world, rank, dev.index)
-            buf_ret = vb.PeerBuffer(ret_bytes, world, rank, dev.index)
+            buf_out = vb.PeerBuffer(job_sf * row, world, rank, dev.index)
+            buf_ret = vb.PeerBuffer(job_sf * 4, world, rank, dev.index)
         except Exception as e:  # no IPC / no peer access on this box: fall back to the collective (all ranks fail alike)
             mode, buf_out, buf_ret = "nccl (peer mapping failed: %r)" % (e,), None, None
     if buf_out is not None:
-        allout = buf_out.local.view(rounds, world, chunk_sf, 110 * s)
-        allret = buf_ret.local.view(torch.int32).view(rounds, world, chunk_sf)
+        allout = buf_out.local.view(job_sf, row)
+        allret = buf_ret.local.view(torch.int32)
         allout.fill_(0xEE)
         allret.fill_(-7)
     else:
-        allout = torch.full((rounds, world, chunk_sf, 110 * s), 0xEE, dtype=torch.uint8, device=dev)
-        allret = torch.full((rounds, world, chunk_sf), -7, dtype=torch.int32, device=dev)
+        allout = torch.full((job_sf, row), 0xEE, dtype=torch.uint8, device=dev)
+        allret = torch.full((job_sf,), -7, dtype=torch.int32, device=dev)
     barrier()  # every rank's arrays are pre-filled before anybody stores into them
+
+    def region(j):  # rows of round j: `world` slices of sizes[j] superframes side by side
+        return offs[j] * world, (offs[j] + sizes[j]) * world
+
+    def mine(j, r=rank):  # rank r's slice of round j
+        lo = offs[j] * world + r * sizes[j]
+        return lo, lo + sizes[j]
+
     others = [r for r in range(world) if r != rank]
-    # two alternating compute streams only when a round is a fraction of the resident set and no collective kernel has
-    # to find room between them: whole-pass rounds (N <= 2) lose nothing to the tail and run ~5 % faster back to back on
-    # one stream (measured, N = 1), and with two streams the next round's blocks fill every slot the previous round
-    # frees, which starves the large blocks of an NCCL kernel until that grid is exhausted (measured, N = 8)
-    nstreams = int(os.environ.get("BENCH_C4_STREAMS", "2" if (chunks_resident > 1 and not mode.startswith("nccl")) else "1"))
+    nstreams = int(os.environ.get("BENCH_C4_STREAMS", "1"))
     comp = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
     comm = torch.cuda.Stream(device=dev, priority=-1)
     main = torch.cuda.current_stream()
@@ -779,21 +793,22 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
             st.wait_stream(main)
         for j in range(rounds):
             st = comp[j % nstreams]
-            c = j % chunks_resident
-            sy = syms[c * chunk_sf * 5:(c + 1) * chunk_sf * 5]
+            sy = syms[starts[j] * 5:(starts[j] + sizes[j]) * 5]
+            lo, hi = mine(j)
+            o, r_ = allout[lo:hi], allret[lo:hi]
             if gather and mode == "peer":
-                vb.dabplus_decode_superframes_device_bcast(f, sy, allout[j, rank], allret[j, rank],
-                                                           [buf_out.peer_ptr(r, allout[j, rank]) for r in others],
-                                                           [buf_ret.peer_ptr(r, allret[j, rank]) for r in others], st)
+                vb.dabplus_decode_superframes_device_bcast(f, sy, o, r_, [buf_out.peer_ptr(p, o) for p in others],
+                                                           [buf_ret.peer_ptr(p, r_) for p in others], st)
                 continue
-            vb.dabplus_decode_superframes_device(f, sy, allout[j, rank], allret[j, rank], st)
+            vb.dabplus_decode_superframes_device(f, sy, o, r_, st)
             if gather and world > 1:
                 done = torch.cuda.Event()
                 done.record(st)
                 comm.wait_event(done)
+                g0, g1 = region(j)
                 with torch.cuda.stream(comm):
-                    dist.all_gather_into_tensor(allout[j].view(-1), allout[j, rank].view(-1))
-                    dist.all_gather_into_tensor(allret[j].view(-1), allret[j, rank].view(-1))
+                    dist.all_gather_into_tensor(allout[g0:g1].view(-1), o.view(-1))
+                    dist.all_gather_into_tensor(allret[g0:g1], r_)
         for st in comp + [comm]:
             main.wait_stream(st)
         if gather and mode == "peer":
@@ -813,43 +828,46 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     ms_nogather = reduce_ranks(run_job(False))
     barrier()
 
-    # ---- checks: accepted superframes equal the transmitted payload; every rank's slice of the gathered array is
-    # what that rank decoded; a slice is compared bit for bit with the CPU reference chain ------------------------
+    # ---- checks: accepted superframes equal the transmitted payload; what this rank holds of every peer is what that
+    # peer decoded; a slice is compared bit for bit with the CPU reference chain ----------------------------------
     run_job(True)
-    mine_out, mine_ret = allout[:, rank], allret[:, rank]
-    nres = chunks_resident
-    ok = mine_ret[:nres] >= 0
-    pay = payload.view(nres, chunk_sf, 110 * s)
-    wrong = int((mine_out[:nres][ok] != pay[ok]).any(dim=1).sum().item())
+    lo, hi = mine(0)
+    ok = allret[lo:hi] >= 0
+    pay = payload[starts[0]:starts[0] + sizes[0]]
+    wrong = int((allout[lo:hi][ok] != pay[ok]).any(dim=1).sum().item())
     accepted = int(ok.sum().item())
     if world > 1:
-        # what this rank holds of every peer must be what that peer decoded: compare per-(round, rank) checksums of the
-        # gathered array with the checksums each producer computes over its own slices (a checksum of checksums)
+        # compare per-(round, rank) checksums of the gathered array with the checksums each producer computes over its
+        # own slices (a checksum of checksums)
         barrier()
-        local = torch.stack([torch.stack([torch.stack([a[j, r].sum(dtype=torch.int64) for r in range(world)]) for j in range(rounds)])
-                             for a in (allout, allret)])  # [2, rounds, world] as seen here
-        mine = local[:, :, rank].contiguous()
-        everyone = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(everyone.view(-1), mine.view(-1))
+
+        def sums(a):
+            return torch.stack([torch.stack([a[mine(j, r)[0]:mine(j, r)[1]].sum(dtype=torch.int64) for r in range(world)])
+                                for j in range(rounds)])
+
+        local = torch.stack([sums(allout), sums(allret)])  # [2, rounds, world] as seen here
+        own = local[:, :, rank].contiguous()
+        everyone = torch.empty((world,) + tuple(own.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(everyone.view(-1), own.view(-1))
         wrong += int((everyone.permute(1, 2, 0) != local).sum().item()) + int((allret == -7).sum().item())
-    nsl = min(chunk_sf, args.parity_superframes // 8)
-    h_syms = syms[: nsl * 5].cpu().numpy()
+    nsl = min(sizes[0], args.parity_superframes // 8)
+    h_syms = syms[starts[0] * 5:(starts[0] + nsl) * 5].cpu().numpy()
     dec = chk.deconvolve_batch(f, h_syms, chk_threads)
     c_out, c_ret = chk.rs_batch(dec.reshape(nsl, 120 * s), s, fill=0xEE, nthreads=chk_threads)
     parity["frames_checked"] += nsl * 5
     parity["superframes_checked"] += nsl
-    parity["mismatches"] += int((c_ret != mine_ret[0, :nsl].cpu().numpy()).sum()) + \
-        int((c_out != mine_out[0, :nsl].cpu().numpy()).any(axis=1).sum()) + wrong
+    parity["mismatches"] += int((c_ret != allret[lo:lo + nsl].cpu().numpy()).sum()) + \
+        int((c_out != allout[lo:lo + nsl].cpu().numpy()).any(axis=1).sum()) + wrong
     frames = job_sf * 5
     gathered = int(allout.numel() + 4 * allret.numel()) if world > 1 else 0
-    del mine_out, mine_ret, allout, allret
+    del allout, allret, ok, pay
     if buf_out is not None:
         buf_out.close()
         buf_ret.close()
     return {
         "workload": "BASELINE configs[4]: %d MSC frames (F=3072) -> %d DAB+ superframes (s=16), Viterbi + RS check on "
                     "device, Eb/N0=4 dB, 0-3 byte errors per codeword before the convolutional encoder" % (frames, job_sf),
-        "scaling": "strong", "n_gpus": world, "rounds": rounds, "chunk_superframes": chunk_sf,
+        "scaling": "strong", "n_gpus": world, "rounds": rounds, "round_superframes": sizes,
         "resident_frames_per_gpu": res_sf * 5,
         "ms_total": ms_gather, "ms_total_without_gather": ms_nogather,
         "frames_per_s": frames / (ms_gather * 1e-3), "superframes_per_s": job_sf / (ms_gather * 1e-3),

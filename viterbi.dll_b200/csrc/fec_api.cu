@@ -288,6 +288,16 @@ size_t rs_chunk_bytes() {
 bool vit_args_ok(unsigned framebits) { return !(framebits & 1u) && framebits <= VITERBI_B200_MAX_FRAMEBITS; }
 
 // Does a launch of n frames go to the two-frames-per-thread throughput kernel (else: warp-per-frame kernel)?
+// VITERBI_B200_PUNCT_SEPARATE=1: punctured input is expanded by the separate depuncturing kernel even where the
+// throughput kernel could do it in its symbol fetch (A/B measurements)
+bool punct_fused() {
+    static const bool separate = [] {
+        const char* env = getenv("VITERBI_B200_PUNCT_SEPARATE");
+        return env && *env == '1';
+    }();
+    return !separate;
+}
+
 bool uses_pair_kernel(size_t n, unsigned framebits) {
     const int mode = g_vit_kernel.load();
     return mode == FEC_VITERBI_PAIR || (mode == FEC_VITERBI_AUTO && n >= vit_warp_kernel_max_frames(framebits));
@@ -500,7 +510,7 @@ int vit_host(unsigned framebits, const void* syms, SymFormat fmt, size_t n, uint
                 rc = FEC_ERR_DEVICE;
                 break;
             }
-            if (uses_pair_kernel(m, framebits)) {
+            if (punct_fused() && uses_pair_kernel(m, framebits)) {
                 // the throughput kernel expands the rows in its symbol fetch (d_aux carries kPunctSlackBytes of slack)
                 rc = vit_device_punctured(st, framebits, (const uint8_t*)s.d_aux, rx_per_frame, (const uint8_t*)g_pipe.d_idx + idx_bytes,
                                           erasure, m, (uint8_t*)s.d_out, s.stream, s.d_scratch, s.scratch_cap);
@@ -1094,7 +1104,7 @@ int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint
     if (!st) return FEC_ERR_DEVICE;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
-    if (uses_pair_kernel(n, framebits)) {
+    if (punct_fused() && uses_pair_kernel(n, framebits)) {
         // Fused path: the throughput kernel expands the rows in its symbol fetch.  Its fetch may touch up to
         // kPunctSlackBytes past a row, which for every row but the last one is simply the next row; the last row
         // is read from a padded copy, so nothing is assumed about what follows the caller's buffer.

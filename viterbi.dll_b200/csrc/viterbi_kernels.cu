@@ -141,8 +141,12 @@ __device__ __forceinline__ void traceback(const uint4* __restrict__ dec, uint32_
 // 8 x (transmitted symbols among the first four), .z = two byte-permute selectors that spread the run over the
 // two step words and put the erasure byte everywhere else.  A thread reads the three aligned words that hold its
 // run of at most eight bytes (rows are dense, so a row starts at any byte), funnel-shifts them into place and
-// expands: ~11 instructions per frame and iteration instead of a separate pass that writes and re-reads the
-// expanded 4(F+6) bytes per frame.  The rows must be followed by 16 readable bytes (the launcher sees to that).
+// expands: ~22 more instructions per iteration instead of a separate pass that writes and re-reads the expanded
+// 4(F+6) bytes per frame.  Measured on device-resident input (FIC 65,536 / MSC 262,144 frames, half of the symbols
+// punctured): 1.25x / 1.12x the unpunctured time, against 1.44x / 1.52x with the separate depuncturing kernel in
+// front.  What is left is the load/store unit: three uncoalesced 4-byte loads per frame and iteration (96 sectors
+// per warp instruction pair against 32 for the plain row fetch).  The last row is read from a padded copy when the
+// buffer may end right behind it (last_row).
 template <bool kWordStores, bool kPunct>
 __global__ void __launch_bounds__(kVitThreads, kVitMinBlocks)
 viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
@@ -213,6 +217,8 @@ viterbi_pair_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
             uint4 en = make_uint4(0u, 0u, 0u, 0u);
             uint32_t wa[3] = {0u, 0u, 0u}, wb[3] = {0u, 0u, 0u};
             if (kPunct) {
+                // (loading the table entry one iteration earlier, so that the fetch addresses never wait for it, was
+                // measured and was slower: 7.04 vs 6.30 ms on the MSC batch -- four more registers live across the steps)
                 if (t + 2 < steps) {
                     en = __ldg(ptab + (t >> 1) + 1);
                     fetch_run(alA, misA, en.x, wa);
