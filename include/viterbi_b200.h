@@ -128,7 +128,7 @@ int rs_check_superframe_batch_device(const uint8_t* d_in, unsigned int RSDims, s
  * syms [nsf * 5][4*(F+6)] soft symbols -> Viterbi -> [nsf][120*s] superframes (s = F/192) -> RS check
  * -> out [nsf][110*s] (same partial-write rule as RScheckSuperframe), ret [nsf].  framebits must be a
  * multiple of 192.  (The DAB energy-dispersal descrambler that sits between the two calls in a full
- * receiver is not part of viterbi.dll and is not applied.) */
+ * receiver is not part of viterbi.dll; it is applied only when fec_set_energy_dispersal(1) was called.) */
 int dabplus_decode_superframes(unsigned int framebits, const uint8_t* syms, size_t nsf, uint8_t* out, int32_t* ret);
 int dabplus_decode_superframes_device(unsigned int framebits, const uint8_t* d_syms, size_t nsf, uint8_t* d_out,
                                       int32_t* d_ret, void* stream);
@@ -159,6 +159,13 @@ int fec_get_devices(int* ordinals, int capacity);
  * (each d_all[j] holds count * bytes_per_shard bytes on device j).  Enqueued on streams[i] (cudaStream_t of
  * device i; streams == NULL or an entry NULL = that device's default stream); the caller synchronises. */
 int fec_allgather_device(const void* const* d_shard, void* const* d_all, size_t bytes_per_shard, void* const* streams);
+
+/* Energy dispersal (ETSI EN 300 401 clause 10): a DAB transmitter XORs every logical frame with the PRBS of
+ * X^9 + X^5 + 1 (restarted with all ones per frame) in front of the convolutional encoder, and a receiver removes it
+ * between deconvolve() and RScheckSuperframe() -- QIRX does that itself, it is not part of viterbi.dll.  With this
+ * option on (process-wide, default off) the chained dabplus_decode_superframes* calls remove it on the device, so
+ * the chain can be fed real sub-channel symbols.  deconvolve / the batch Viterbi calls are never affected. */
+int fec_set_energy_dispersal(int on);
 
 /* Gather fused into the producing kernel: the same calls as rs_check_superframe_batch_device() /
  * dabplus_decode_superframes_device(), and every result byte and return value the RS kernel stores into d_out /

@@ -63,3 +63,13 @@ def test_torch_generators_agree_with_the_decoders(port):
     dec = port.deconvolve_batch(384, syms.numpy()).reshape(6, -1)
     out, ret = port.rs_batch(dec, 2, fill=0xEE)
     assert (ret >= 0).all() and np.array_equal(out, payload.numpy())
+
+
+def test_energy_dispersal_prbs_known_prefix():
+    """ETSI EN 300 401 clause 10: the PRBS of X^9 + X^5 + 1 from an all-ones register starts 0000 0111 1011 1110;
+    period 511."""
+    from viterbi_dll_b200 import dabgen
+
+    p = dabgen.energy_dispersal_prbs(1100)
+    assert "".join(map(str, p[:16])) == "0000011110111110"
+    assert np.array_equal(p[:511], p[511:1022]) and not np.array_equal(p[:100], p[100:200])

@@ -197,6 +197,35 @@ def test_dabplus_pipeline_recovers_payload_end_to_end(vb):
     assert np.array_equal(out[ok], payload[ok])
 
 
+def test_dabplus_pipeline_with_energy_dispersal(vb, checker):
+    """fec_set_energy_dispersal(1): frames scrambled by the transmitter (ETSI EN 300 401 clause 10) come out of the
+    chained call like unscrambled frames come out of it with the option off -- the reference chain with the PRBS
+    removed on the host in between."""
+    import torch
+
+    for framebits, nsf in ((3072, 300), (768, 1200), (192, 500)):
+        s = framebits // 192
+        syms, payload, _ = dabgen.make_superframe_frames(nsf, framebits, 3.5, seed=framebits + 1, max_err=4, scramble=True)
+        decoded = checker.deconvolve_batch(framebits, syms)
+        prbs = np.packbits(dabgen.energy_dispersal_prbs(framebits), bitorder="big")
+        want_out, want_ret = checker.rs_batch((decoded ^ prbs[None, :]).reshape(nsf, 120 * s), s, fill=0xEE)
+        try:
+            vb.set_energy_dispersal(True)
+            out, ret = vb.dabplus_decode_superframes(framebits, syms, fill=0xEE)
+            d_out = torch.full((nsf, 110 * s), 0xEE, dtype=torch.uint8, device="cuda")
+            d_out, d_ret = vb.dabplus_decode_superframes_device(framebits, torch.from_numpy(syms).cuda(), d_out)
+            torch.cuda.synchronize()
+        finally:
+            vb.set_energy_dispersal(False)
+        assert np.array_equal(ret, want_ret) and np.array_equal(out, want_out)
+        assert np.array_equal(d_ret.cpu().numpy(), want_ret) and np.array_equal(d_out.cpu().numpy(), want_out)
+        ok = want_ret >= 0
+        assert ok.mean() > 0.5 and np.array_equal(out[ok], payload[ok])  # and it is the transmitted payload
+        # with the option off the same symbols are garbage for the RS stage
+        _, ret_off = vb.dabplus_decode_superframes(framebits, syms, fill=0xEE)
+        assert (ret_off < 0).mean() > 0.9
+
+
 def test_dabplus_pipeline_argument_checks(vb):
     assert vb.lib.dabplus_decode_superframes(100, None, 1, None, None) == vb.FEC_ERR_ARG  # not a multiple of 192
     assert vb.lib.dabplus_decode_superframes(3072, None, 0, None, None) == vb.FEC_OK

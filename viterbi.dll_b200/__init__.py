@@ -74,6 +74,7 @@ _SIGNATURES = {
     "fec_memcpy_d2h": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "fec_device_synchronize": (ctypes.c_int, []),
     "fec_set_viterbi_kernel": (ctypes.c_int, [ctypes.c_int]),
+    "fec_set_energy_dispersal": (ctypes.c_int, [ctypes.c_int]),
     "fec_kernel_launches": (ctypes.c_ulonglong, []),
 }
 
@@ -425,6 +426,11 @@ def dabplus_decode_superframes_device_bcast(framebits: int, syms, out, ret, out_
 
 
 VITERBI_AUTO, VITERBI_PAIR, VITERBI_WARP = 0, 1, 2
+
+
+def set_energy_dispersal(on: bool) -> None:
+    """dabplus_* calls: remove the DAB energy dispersal (PRBS X^9 + X^5 + 1 per logical frame) between Viterbi and RS."""
+    _check(lib.fec_set_energy_dispersal(1 if on else 0), "fec_set_energy_dispersal")
 
 
 def set_viterbi_kernel(mode: int) -> None:

@@ -39,6 +39,7 @@ std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_save_mode{0};
 std::atomic<int> g_device{-1};  // -1: use the calling thread's current device
 std::atomic<int> g_vit_kernel{FEC_VITERBI_AUTO};
+std::atomic<int> g_descramble{0};  // dabplus_* calls: remove the DAB energy dispersal between Viterbi and RS
 std::atomic<unsigned> g_generation{1};  // bumped when initialize() had to reset a device: staging state of older generations is dead
 thread_local std::string t_error;
 thread_local int t_device = -1;  // per-thread device (fec_set_thread_device, multi-device workers); wins over g_device
@@ -111,7 +112,7 @@ bool init_device(DeviceState* st, int dev) {
     cudaDeviceProp prop;
     if (fail(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return false;
     st->num_sms = prop.multiProcessorCount;
-    if (fail(rs_upload_tables(), "RS table upload") || fail(viterbi_configure_device(), "viterbi kernel attributes") ||
+    if (fail(rs_upload_tables(), "RS table upload") || fail(descramble_upload_table(), "PRBS table upload") || fail(viterbi_configure_device(), "viterbi kernel attributes") ||
         fail(rs_configure_device(), "rs kernel attributes"))
         return false;
     // the table upload ran on the legacy default stream; the kernels run on non-blocking streams, which do not
@@ -940,6 +941,10 @@ int dabplus_host(unsigned framebits, const uint8_t* syms, size_t nsf, uint8_t* o
         rc = vit_device(st, framebits, (const uint8_t*)sl.d_in, m * 5, d_bits, sl.stream, d_bits + bits_bytes,
                         sl.scratch_cap - bits_bytes);
         if (rc != FEC_OK) break;
+        if (g_descramble.load() && fail(launch_descramble(d_bits, m * 5, framebits, st->num_sms, sl.stream), "descramble kernel")) {
+            rc = FEC_ERR_DEVICE;
+            break;
+        }
         if (fail(launch_rs_superframes(d_bits, (uint8_t*)sl.d_out, (int32_t*)sl.d_aux, d_orig, m, rsdims, st->num_sms, sl.stream),
                  "rs kernel launch") ||
             fail(cudaMemcpyAsync(out + done * out_row, sl.d_out, m * out_row, cudaMemcpyDeviceToHost, sl.stream), "D2H") ||
@@ -1196,6 +1201,8 @@ int dabplus_decode_superframes_device_bcast(unsigned int framebits, const uint8_
     void* d_bits = nullptr;
     if (fail(cudaMallocAsync(&d_bits, nsf * 120 * (size_t)rsdims, s), "cudaMallocAsync(decoded frames)")) return FEC_ERR_DEVICE;
     int rc = vit_device(st, framebits, d_syms, nsf * 5, (uint8_t*)d_bits, s, nullptr, 0);
+    if (rc == FEC_OK && g_descramble.load() && fail(launch_descramble((uint8_t*)d_bits, nsf * 5, framebits, st->num_sms, s), "descramble kernel"))
+        rc = FEC_ERR_DEVICE;
     if (rc == FEC_OK && fail(launch_rs_superframes((const uint8_t*)d_bits, d_out, d_ret, nullptr, nsf, rsdims, st->num_sms, s,
                                                    d_out_copies, d_ret_copies, ncopies),
                              "rs kernel launch"))
@@ -1466,6 +1473,11 @@ int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes) {
 }
 
 int fec_device_synchronize(void) { return fail(cudaDeviceSynchronize(), "cudaDeviceSynchronize") ? FEC_ERR_DEVICE : FEC_OK; }
+
+int fec_set_energy_dispersal(int on) {
+    g_descramble.store(on ? 1 : 0);
+    return FEC_OK;
+}
 
 int fec_set_viterbi_kernel(int mode) {
     if (mode < FEC_VITERBI_AUTO || mode > FEC_VITERBI_WARP) return bad_arg("unknown kernel mode");

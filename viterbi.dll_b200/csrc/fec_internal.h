@@ -46,6 +46,8 @@ cudaError_t launch_viterbi_pair_punctured(const uint8_t* d_rx, uint32_t rx_per_f
 void punct_table(uint32_t framebits, const uint8_t* keep, uint32_t* table);  // (F+6)/2 entries of 4 words
 cudaError_t launch_depuncture(const uint8_t* d_rx, size_t rx_per_frame, const int32_t* d_idx, uint32_t framebits,
                               uint32_t erasure, uint8_t* d_syms, size_t nframes, int num_sms, cudaStream_t stream);
+cudaError_t descramble_upload_table();
+cudaError_t launch_descramble(uint8_t* d_bits, size_t nframes, uint32_t framebits, int num_sms, cudaStream_t stream);
 cudaError_t launch_compact_symbols(const uint32_t* d_in, uint8_t* d_out, size_t nsymbols, int num_sms,
                                    cudaStream_t stream);
 

@@ -279,6 +279,44 @@ __global__ void __launch_bounds__(256) depuncture_kernel(const uint8_t* __restri
     }
 }
 
+// Energy-dispersal descrambler (the step a DAB receiver performs between deconvolve() and
+// RScheckSuperframe(); ETSI EN 300 401 clause 10): every decoded logical frame is XORed with the PRBS of
+// X^9 + X^5 + 1 restarted (all ones) at the start of the frame.  The sequence does not depend on the frame length,
+// so one table of kMaxFramebits / 8 bytes serves every F.  An element-wise pass over F/8 bytes per frame (0.4 % of
+// the bytes the Viterbi kernel moves), only used by the chained dabplus_* calls when the option is on.
+__constant__ uint32_t c_prbs_words[kMaxFramebits / 32];
+
+__global__ void __launch_bounds__(256) descramble_kernel(uint8_t* __restrict__ bits, size_t nframes, uint32_t bytes_per_frame) {
+    const size_t total = nframes * bytes_per_frame;
+    const uint8_t* prbs = reinterpret_cast<const uint8_t*>(c_prbs_words);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        bits[i] ^= prbs[i % bytes_per_frame];
+}
+
+cudaError_t descramble_upload_table() {
+    static uint32_t words[kMaxFramebits / 32];
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(words);
+    unsigned reg = 0x1FF;  // nine ones; bit 8 = oldest
+    for (uint32_t i = 0; i < kMaxFramebits; i++) {
+        const unsigned b = ((reg >> 8) ^ (reg >> 4)) & 1u;
+        reg = ((reg << 1) | b) & 0x1FF;
+        if ((i & 7) == 0) bytes[i >> 3] = 0;
+        bytes[i >> 3] |= (uint8_t)(b << (7 - (i & 7)));  // MSB first, like the decoder's output bytes
+    }
+    return cudaMemcpyToSymbol(c_prbs_words, words, sizeof words);
+}
+
+cudaError_t launch_descramble(uint8_t* d_bits, size_t nframes, uint32_t framebits, int num_sms, cudaStream_t stream) {
+    if (nframes == 0 || framebits < 8) return cudaSuccess;
+    const size_t total = nframes * (framebits / 8);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    descramble_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_bits, nframes, framebits / 8);
+    count_launch();
+    return cudaGetLastError();
+}
+
 size_t viterbi_scratch_bytes(int grid_blocks, uint32_t framebits) {
     return kVitScratchHeader + (size_t)grid_blocks * (size_t)(framebits + 6) * 32 * sizeof(uint4);
 }

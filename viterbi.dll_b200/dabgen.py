@@ -320,12 +320,25 @@ def make_superframes_torch(n: int, s: int, seed: int, device, max_err: int = 7, 
 # ---------------------------------------------------------------------------
 # DAB+ pipeline traffic: RS-protected superframes carried in 5 convolutionally coded frames each
 # ---------------------------------------------------------------------------
-def make_superframe_frames(nsf: int, framebits: int, ebn0_db: float, seed: int, max_err: int = 0):
+def energy_dispersal_prbs(nbits: int) -> np.ndarray:
+    """DAB energy-dispersal sequence (ETSI EN 300 401 clause 10): PRBS of P(X) = X^9 + X^5 + 1, register
+    initialised to all ones at the start of every logical frame.  First bits: 0000 0111 1011 1110 ..."""
+    reg = [1] * 9
+    out = np.empty(nbits, dtype=np.uint8)
+    for i in range(nbits):
+        b = reg[8] ^ reg[4]
+        out[i] = b
+        reg = [b] + reg[:8]
+    return out
+
+
+def make_superframe_frames(nsf: int, framebits: int, ebn0_db: float, seed: int, max_err: int = 0, scramble: bool = False):
     """-> (symbols u8 [nsf*5, 4*(F+6)], clean payload [nsf, 110*s], transmitted superframes [nsf, 120*s]).
 
     A superframe of s = F/192 interleaved RS(120,110) codewords is 5*F/8 bytes = the payload of five
     consecutive frames.  max_err > 0 additionally corrupts bytes BEFORE the convolutional encoder
-    (errors the Viterbi decoder cannot remove), so the RS stage has work even on a clean channel."""
+    (errors the Viterbi decoder cannot remove), so the RS stage has work even on a clean channel.
+    scramble: apply the DAB energy dispersal to every logical frame, as a real transmitter does."""
     if framebits % 192:
         raise ValueError("framebits must be a multiple of 192")
     s = framebits // 192
@@ -336,6 +349,8 @@ def make_superframe_frames(nsf: int, framebits: int, ebn0_db: float, seed: int, 
         cw = rs_inject_errors(cw, rng.integers(0, max_err + 1, size=nsf * s), rng)
     sf = rs_interleave(cw, s)  # [nsf, 120*s]
     bits = np.unpackbits(sf.reshape(nsf * 5, framebits // 8), axis=1, bitorder="big")
+    if scramble:  # the transmitter's energy dispersal, per logical frame, in front of the convolutional encoder
+        bits = bits ^ energy_dispersal_prbs(framebits)[None, :]
     syms = soft_symbols(conv_encode(bits), ebn0_db, rng)
     payload = np.ascontiguousarray(msg.reshape(nsf, s, RS_K).transpose(0, 2, 1)).reshape(nsf, RS_K * s)
     return syms, payload, sf
