@@ -68,7 +68,7 @@ def pair_kernel_loop(funcs, word_stores=True, punctured=False):
 
 def warp_kernel_loop(funcs):
     """The 10-step forward loop of viterbi_warp_kernel: the smallest loop with ten butterfly shuffles."""
-    name = next(n for n in funcs if "viterbi_warp_kernel" in n)
+    name = next(n for n in funcs if "viterbi_warp_kernel" in n and "ILi128E" in n)  # the latency shape (four warps per block)
     ins = funcs[name]
     best = None
     for lo, hi in loops(ins):

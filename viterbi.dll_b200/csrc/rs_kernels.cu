@@ -82,6 +82,8 @@ struct RsCopies {
 #ifndef RS_MIN_BLOCKS
 #define RS_MIN_BLOCKS 8
 #endif
+// kCopies: the launch has extra destinations (RsCopies); the plain instantiation carries none of that code.
+template <bool kCopies>
 __global__ void __launch_bounds__(kRsThreads, RS_MIN_BLOCKS)
 rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ ret,
                      const uint8_t* __restrict__ orig, unsigned long long nsf, uint32_t s, uint32_t sf_per_block,
@@ -138,7 +140,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
         for (uint32_t n = tid; n < nloc; n += blockDim.x) {
             const int32_t r = (s_fail[n] < (int)s) ? -1 : s_sum[n];
             ret[sf0 + n] = r;
-            for (int c = 0; c < copies.n; c++) copies.ret[c][sf0 + n] = r;
+            for (int c = 0; kCopies && c < copies.n; c++) copies.ret[c][sf0 + n] = r;
         }
         // ---- write back the 110*s data bytes; columns >= first failure stay untouched -------------
         uint8_t* dst = out + sf0 * sf_out;
@@ -154,7 +156,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                 const size_t doff = (size_t)(d - out);  // the same bytes go to every extra copy (peer buffers over NVLink)
                 if (tid < nhead) {
                     d[tid] = t[tid];
-                    for (int c = 0; c < copies.n; c++) copies.out[c][doff + tid] = t[tid];
+                    for (int c = 0; kCopies && c < copies.n; c++) copies.out[c][doff + tid] = t[tid];
                 }
                 const size_t nwords = (sf_out - nhead) / 4;
                 const uint32_t toff = (uint32_t)(reinterpret_cast<uintptr_t>(t + nhead) & 3);
@@ -163,11 +165,11 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                 for (size_t w = tid; w < nwords; w += blockDim.x) {
                     const uint32_t v = __byte_perm(tw[w], tw[w + 1], sel);
                     reinterpret_cast<uint32_t*>(d + nhead)[w] = v;
-                    for (int c = 0; c < copies.n; c++) reinterpret_cast<uint32_t*>(copies.out[c] + doff + nhead)[w] = v;
+                    for (int c = 0; kCopies && c < copies.n; c++) reinterpret_cast<uint32_t*>(copies.out[c] + doff + nhead)[w] = v;
                 }
                 for (size_t i = nhead + nwords * 4 + tid; i < sf_out; i += blockDim.x) {
                     d[i] = t[i];
-                    for (int c = 0; c < copies.n; c++) copies.out[c][doff + i] = t[i];
+                    for (int c = 0; kCopies && c < copies.n; c++) copies.out[c][doff + i] = t[i];
                 }
             } else if (orig == nullptr) {
                 // i % s through a multiply-high (s is launch-uniform; exact for i < 2^17, s <= 1024)
@@ -176,7 +178,7 @@ rs_superframe_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                     for (uint32_t i = tid; i < (uint32_t)sf_out; i += blockDim.x)
                         if (i - __umulhi(i, inv_s) * s < fail) {
                             d[i] = t[i];
-                            for (int c = 0; c < copies.n; c++) copies.out[c][doff + i] = t[i];
+                            for (int c = 0; kCopies && c < copies.n; c++) copies.out[c][doff + i] = t[i];
                         }
                 }
             }
@@ -306,8 +308,10 @@ cudaError_t rs_upload_tables() {
 
 // opt-in to the largest tile (one superframe of kRsMaxDims codewords) once per device, see viterbi_configure_device()
 cudaError_t rs_configure_device() {
-    return cudaFuncSetAttribute(rs_superframe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)rs_smem_bytes(kRsMaxDims, 1));
+    const int worst = (int)rs_smem_bytes(kRsMaxDims, 1);
+    cudaError_t e = cudaFuncSetAttribute(rs_superframe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, worst);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(rs_superframe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, worst);
 }
 
 cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* d_ret, const uint8_t* d_orig,
@@ -319,7 +323,7 @@ cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* 
     unsigned long long nblk = (nsf + spb - 1) / spb;
     // persistent grid: exactly the blocks that are resident at once, so each block stages the tables once
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rs_superframe_kernel, kRsThreads, smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rs_superframe_kernel<false>, kRsThreads, smem) != cudaSuccess ||
         per_sm < 1) {
         (void)cudaGetLastError();
         per_sm = 4;
@@ -333,7 +337,10 @@ cudaError_t launch_rs_superframes(const uint8_t* d_in, uint8_t* d_out, int32_t* 
         copies.ret[copies.n] = extra_ret[c];
         copies.n++;
     }
-    rs_superframe_kernel<<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, d_orig, nsf, s, spb, copies);
+    if (copies.n > 0)
+        rs_superframe_kernel<true><<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, d_orig, nsf, s, spb, copies);
+    else
+        rs_superframe_kernel<false><<<(unsigned)nblk, kRsThreads, smem, stream>>>(d_in, d_out, d_ret, d_orig, nsf, s, spb, copies);
     count_launch();
     return cudaGetLastError();
 }

@@ -145,16 +145,21 @@ __device__ __forceinline__ void warp_trace_step(uint32_t& ln, uint32_t& w, const
 
 // done_flag: when not null (single-frame drop-in on the caller's pinned bounce buffer) the block writes 1 there
 // after its output bytes are visible system-wide; the host polls the flag instead of synchronising the stream.
-__global__ void __launch_bounds__(kVitWarpThreads) viterbi_warp_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
-                                                                         unsigned long long nframes, uint32_t framebits,
-                                                                         uint32_t* done_flag) {
+// kThreads: 128 (latency shape: four warps stage / trace / collect) or 32 (throughput shape: four times as many
+// frames resident per SM).  A template parameter, not blockDim.x: with a run-time block size ptxas scheduled the
+// forward loop differently and the single-frame call lost 12 % (36.6 -> 40.1 us at F = 768).
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) viterbi_warp_kernel(const uint8_t* __restrict__ syms, uint8_t* __restrict__ out,
+                                                                  unsigned long long nframes, uint32_t framebits,
+                                                                  uint32_t* done_flag) {
     extern __shared__ __align__(16) uint8_t wsmem[];
-    const uint32_t steps = framebits + 6, tid = threadIdx.x, lane = tid & 31u, nthreads = blockDim.x;  // 32 or 128
+    constexpr uint32_t nthreads = kThreads;
+    const uint32_t steps = framebits + 6, tid = threadIdx.x, lane = tid & 31u;
     uint32_t* s_sym = reinterpret_cast<uint32_t*>(wsmem);  // [steps + 2] 4 symbols per step (+ a readable pad word, never used); reused by the traceback
     uint2* s_dec = reinterpret_cast<uint2*>(wsmem + 4 * (size_t)(steps + 2));  // [steps] {even, odd} ballots
     const size_t outbytes = (framebits + 7) / 8;
-    __shared__ uint32_t s_state[kVitWarpThreads + 1];  // end state of every traceback segment (0 = no segment)
-    if (tid == 0) s_state[kVitWarpThreads] = 0;
+    __shared__ uint32_t s_state[kThreads + 1];  // end state of every traceback segment (0 = no segment)
+    if (tid == 0) s_state[kThreads] = 0;
 
     // per-lane constants of the five phases: the branch mask (const.asm:35-49 restated: 0xFF where the expected
     // code bit is 1) of butterfly rotl5(lane, phase), and the selectors that build {A, A} / {B, B} from the lane's
@@ -335,8 +340,10 @@ size_t viterbi_warp_smem_bytes(uint32_t framebits) { return 12 * (size_t)(frameb
 // initialisation in fec_api.cu -- not lazily per launch, where concurrent callers with different frame sizes
 // would lower each other's limit.
 cudaError_t viterbi_configure_device() {
-    return cudaFuncSetAttribute(viterbi_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)viterbi_warp_smem_bytes(kMaxFramebits));
+    const int worst = (int)viterbi_warp_smem_bytes(kMaxFramebits);
+    cudaError_t e = cudaFuncSetAttribute(viterbi_warp_kernel<kVitWarpThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, worst);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(viterbi_warp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, worst);
 }
 
 cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned long long nframes, uint32_t framebits,
@@ -346,10 +353,12 @@ cudaError_t launch_viterbi_warp(const uint8_t* d_syms, uint8_t* d_out, unsigned 
     // Latency shape (a few frames): four warps per block, so that staging, the speculative traceback and the output
     // pass are spread wide.  Throughput shape (more frames than two per SM): one warp per block -- only warp 0 runs the
     // trellis, and a 32-thread block lets four times as many frames be resident per SM.
-    const unsigned threads = nframes <= (unsigned long long)num_sms * 2 ? kVitWarpThreads : 32u;
     const unsigned long long cap = (unsigned long long)num_sms * 32;
     const unsigned grid = (unsigned)(nframes < cap ? nframes : cap);
-    viterbi_warp_kernel<<<grid, threads, smem, stream>>>(d_syms, d_out, nframes, framebits, done_flag);
+    if (nframes <= (unsigned long long)num_sms * 2)
+        viterbi_warp_kernel<kVitWarpThreads><<<grid, kVitWarpThreads, smem, stream>>>(d_syms, d_out, nframes, framebits, done_flag);
+    else
+        viterbi_warp_kernel<32><<<grid, 32, smem, stream>>>(d_syms, d_out, nframes, framebits, done_flag);
     count_launch();
     return cudaGetLastError();
 }
