@@ -30,6 +30,7 @@ def build(name: str, flags: str) -> None:
             name = "rev_" + rev.replace("/", "_")
         objs = []
         for src, extra in ((vit_src, ["-Xptxas", "-O1"] + shlex.split(flags)),
+                           (os.path.join(CSRC, "viterbi_warp_kernel.cu"), shlex.split(flags)),
                            (os.path.join(CSRC, "rs_kernels.cu"), shlex.split(flags)),
                            (os.path.join(CSRC, "fec_api.cu"), shlex.split(flags))):
             obj = os.path.join(tmp, os.path.basename(src) + ".o")
