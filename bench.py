@@ -707,6 +707,28 @@ def run_b200(args):
     return 0
 
 
+def configs4_round_sizes(my_sf: int, wave_sf: int, res_cap: int):
+    """Superframes per round of one rank's share: whole waves, shrinking towards the end.  The gather of round j hides
+    behind the decoding of round j + 1 as long as it is not much bigger than that round can cover (a wave's results take
+    about a quarter of a wave's decoding time to gather at N = 8), and the gather of the LAST round cannot hide at all --
+    so the last round is the remainder (0.5 .. 1.5 waves), the rounds before it double in size going backwards
+    (2, 4, 8 waves, ...) up to the resident-symbol cap, and the first rounds take what is left in cap-sized pieces."""
+    if my_sf <= wave_sf + wave_sf // 2:
+        return [my_sf]
+    tail = my_sf % wave_sf
+    if tail < wave_sf // 2:
+        tail += wave_sf
+    rev, left, step = [tail], my_sf - tail, 2 * wave_sf
+    while left > 0:
+        sz = min(step, left, res_cap)
+        if 0 < left - sz < wave_sf:  # no sliver in front: give it to this round if the cap allows, else split evenly
+            sz = left if left <= res_cap else (left // 2) // wave_sf * wave_sf
+        rev.append(sz)
+        left -= sz
+        step *= 2
+    return rev[::-1]
+
+
 def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, barrier, reduce_ranks):
     """BASELINE configs[4]: `--configs4-frames` (2^24) MSC frames = 3.36 M DAB+ superframes (s = 16), Viterbi + RS check
     on the device, STRONG scaling: the job is the same whatever N is, and the timed region ends when EVERY rank holds
@@ -715,9 +737,9 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     The job is cut into rounds; in every round each rank decodes one contiguous slice, and the slices of a round sit
     side by side in the result array, so the gather of a round is one contiguous all-gather in natural superframe
     order.  A round is a whole number of WAVES of the persistent Viterbi grid (148 SMs x 16 warps x 64 frames), so
-    cutting the work into rounds costs nothing at the tail of a launch; a rank's share is cut into at least four
-    rounds, the last one the small remainder, because the gather of the last round is the only one that cannot hide
-    behind decoding.  A rank keeps at most 2^21 frames of symbols (25.8 GB) resident and reuses them (206 GB of
+    cutting the work into rounds costs nothing at the tail of a launch; the rounds shrink towards the end
+    (configs4_round_sizes: ..., 4, 2 waves, remainder), because the gather of the last round is the only one that
+    cannot hide behind decoding.  A rank keeps at most 2^21 frames of symbols (25.8 GB) resident and reuses them (206 GB of
     symbols do not fit one GPU; a pass streams far more than the 126 MB L2, so a repeated pass costs what a fresh one
     does).  Gather: NCCL all_gather_into_tensor per round, in place, on a high-priority stream beside ONE compute
     stream (the collective and the next round then become runnable together and the priority puts the collective's
@@ -734,10 +756,8 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     my_sf = -(-total_sf // world)
     wave_sf = (torch.cuda.get_device_properties(dev).multi_processor_count * 16 * 64) // 5  # superframes per wave
     res_cap = max(wave_sf, ((1 << 21) // 5) // wave_sf * wave_sf)  # resident symbols: whole waves, <= 2^21 frames
-    per_round = max(wave_sf, min(res_cap, (my_sf // 4) // wave_sf * wave_sf))
-    sizes = [per_round] * (my_sf // per_round)
-    if my_sf - sum(sizes) > 0:
-        sizes.append(my_sf - sum(sizes))
+    # one rank has nothing to gather: cap-sized rounds (the resident symbols) and the remainder
+    sizes = configs4_round_sizes(my_sf, wave_sf, res_cap) if world > 1 else [res_cap] * (my_sf // res_cap) + ([my_sf % res_cap] if my_sf % res_cap else [])
     rounds = len(sizes)
     offs = [sum(sizes[:j]) for j in range(rounds)]
     res_sf = min(my_sf, res_cap)

@@ -82,3 +82,26 @@ def test_two_rank_partition_and_gather_matches_single_process(tmp_path):
     o, r = port_lib.rs_batch(rx, s_rs, fill=0xEE)
     assert np.array_equal(np.load(tmp_path / "rs_out.npy"), o)
     assert np.array_equal(np.load(tmp_path / "rs_ret.npy"), r)
+
+
+def test_configs4_round_sizes_cover_the_share_in_whole_waves():
+    """bench.py's configs[4] schedule: rounds sum to the rank's share, respect the resident-symbol cap, are whole waves
+    except the last, and shrink towards the end (the last gather is the only exposed one)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wave = 148 * 16 * 64 // 5
+    cap = ((1 << 21) // 5) // wave * wave
+    for world in (1, 2, 3, 4, 8):
+        my = -(-((1 << 24) // 5) // world)
+        sizes = bench.configs4_round_sizes(my, wave, cap)
+        assert sum(sizes) == my and max(sizes) <= cap and min(sizes) > 0
+        assert all(sz % wave == 0 for sz in sizes[:-1])
+        assert wave // 2 <= sizes[-1] <= wave + wave // 2
+        tail = sizes[-4:]
+        assert tail == sorted(tail, reverse=True)
+    for my in (1, 100, wave, wave + wave // 2 + 1, 2 * wave + 5, 14 * wave + 1):
+        sizes = bench.configs4_round_sizes(my, wave, cap)
+        assert sum(sizes) == my and max(sizes) <= cap and min(sizes) > 0
