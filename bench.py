@@ -741,12 +741,16 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     (configs4_round_sizes: ..., 4, 2 waves, remainder), because the gather of the last round is the only one that
     cannot hide behind decoding.  A rank keeps at most 2^21 frames of symbols (25.8 GB) resident and reuses them (206 GB of
     symbols do not fit one GPU; a pass streams far more than the 126 MB L2, so a repeated pass costs what a fresh one
-    does).  Gather: NCCL all_gather_into_tensor per round, in place, on a high-priority stream beside ONE compute
-    stream (the collective and the next round then become runnable together and the priority puts the collective's
+    does).  Gather, default (BENCH_C4_GATHER=dma): after each round the copy engines push the rank's results into
+    every rank's array over NVLink (fec_memcpy_d2d_async on CUDA IPC mappings of the peers' arrays) -- no SM is taken
+    from the decode kernels, measured at N = 8: 50.4 ms against 52.9 with NCCL and 57.9 with the RS kernel's own peer
+    stores (49.1 without any gather).  BENCH_C4_GATHER=nccl: all_gather_into_tensor per round, in place, on a
+    high-priority stream beside ONE compute stream (the collective and the next round then become runnable together and the priority puts the collective's
     few blocks first; with a second compute stream the next round's blocks refill every slot as it frees and the
     collective's large blocks starve until that grid is exhausted -- measured at N = 8: 58.2 vs 53.5 ms).
     BENCH_C4_GATHER=peer uses the fused alternative instead: the RS kernel stores its result tiles into every rank's
-    array itself through CUDA IPC peer mappings (the *_bcast entry points; no collective at all)."""
+    array itself through CUDA IPC peer mappings (the *_bcast entry points; no collective at all).
+    If the IPC mappings cannot be set up the run falls back to NCCL and says so in the line."""
     import torch
     import torch.distributed as dist
 
@@ -774,9 +778,9 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
 
-    mode = os.environ.get("BENCH_C4_GATHER", "nccl") if world > 1 else "none"
+    mode = os.environ.get("BENCH_C4_GATHER", "dma") if world > 1 else "none"
     buf_out = buf_ret = None
-    if mode == "peer":
+    if mode in ("peer", "dma"):
         try:
             buf_out = vb.PeerBuffer(job_sf * row, world, rank, dev.index)
             buf_ret = vb.PeerBuffer(job_sf * 4, world, rank, dev.index)
@@ -803,13 +807,15 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
     nstreams = int(os.environ.get("BENCH_C4_STREAMS", "1"))
     comp = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
     comm = torch.cuda.Stream(device=dev, priority=-1)
+    ncopy = int(os.environ.get("BENCH_C4_COPY_STREAMS", "4"))
+    copy_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(ncopy)] if mode == "dma" else []
     main = torch.cuda.current_stream()
     sync_flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def run_job(gather: bool):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(main)
-        for st in comp + [comm]:
+        for st in comp + [comm] + copy_streams:
             st.wait_stream(main)
         for j in range(rounds):
             st = comp[j % nstreams]
@@ -821,6 +827,16 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
                                                            [buf_ret.peer_ptr(p, r_) for p in others], st)
                 continue
             vb.dabplus_decode_superframes_device(f, sy, o, r_, st)
+            if gather and mode == "dma":
+                # the copy engines push this round's results into every peer's array over NVLink (no SM involved)
+                done = torch.cuda.Event()
+                done.record(st)
+                for k, p in enumerate(others):
+                    cs = copy_streams[k % ncopy]
+                    cs.wait_event(done)
+                    vb.memcpy_d2d_async(buf_out.peer_ptr(p, o), o, o.numel(), cs)
+                    vb.memcpy_d2d_async(buf_ret.peer_ptr(p, r_), r_, 4 * r_.numel(), cs)
+                continue
             if gather and world > 1:
                 done = torch.cuda.Event()
                 done.record(st)
@@ -829,9 +845,9 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
                 with torch.cuda.stream(comm):
                     dist.all_gather_into_tensor(allout[g0:g1].view(-1), o.view(-1))
                     dist.all_gather_into_tensor(allret[g0:g1], r_)
-        for st in comp + [comm]:
+        for st in comp + [comm] + copy_streams:
             main.wait_stream(st)
-        if gather and mode == "peer":
+        if gather and mode in ("peer", "dma"):
             dist.all_reduce(sync_flag)  # on `main`: completes once EVERY rank's kernels (and their peer stores) are done
         end.record(main)
         torch.cuda.synchronize()
@@ -896,6 +912,9 @@ def run_configs4(args, vb, dabgen, chk, chk_threads, parity, dev, rank, world, b
         "gather": {"peer": "inside ms_total: the RS kernel of each rank stores its result tiles into every rank's result array "
                            "over NVLink (CUDA IPC peer mappings, dabplus_decode_superframes_device_bcast); a 4-byte all-reduce "
                            "closes the timed region",
+                   "dma": "inside ms_total: after each round the copy engines push the rank's results into every rank's result "
+                          "array over NVLink (fec_memcpy_d2d_async on CUDA IPC peer mappings, %d copy streams), overlapped with "
+                          "the next round; a 4-byte all-reduce closes the timed region" % ncopy,
                    "none": "single rank: nothing to gather"}.get(mode, "inside ms_total: NCCL all_gather_into_tensor per round on a "
                                                                        "high-priority stream, in place into the full result array, "
                                                                        "overlapped with the next round (%s)" % mode),

@@ -212,6 +212,12 @@ void* fec_device_alloc(size_t bytes);
 void fec_device_free(void* p);
 int fec_memcpy_h2d(void* d_dst, const void* src, size_t bytes);
 int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
+/* Asynchronous device-to-device copy on `stream` (cudaMemcpyAsync, unified addressing): source and destination may
+ * live on different GPUs -- cudaMalloc'ed buffers of one process with fec_enable_peer_access(), or a peer process's
+ * buffer mapped with fec_ipc_import().  The copy engines move the bytes over NVLink without occupying an SM, so a
+ * host can push each shard of results into the peers' arrays while the next batch is being decoded: a third way to
+ * gather (beside fec_allgather_device and the *_bcast calls), and the one that disturbs the decode kernels least. */
+int fec_memcpy_d2d_async(void* d_dst, const void* d_src, size_t bytes, void* stream);
 int fec_device_synchronize(void);
 
 /* Viterbi kernel selection: 0 = automatic (warp-per-frame kernel below 8,192 frames per launch for F <= 1536 and

@@ -106,6 +106,33 @@ def test_allgather_device_from_one_process(vb):
         assert torch.equal(o.cpu(), want)
 
 
+def test_copy_engine_gather_between_devices(vb):
+    """fec_memcpy_d2d_async: every device pushes its shard into every device's array (the gather by the copy engines,
+    no kernel and no collective); on one GPU the same call is a plain device-to-device copy."""
+    import torch
+
+    n = vb.lib.fec_device_count()
+    vb.set_devices(None)
+    if n > 1:
+        assert vb.lib.fec_enable_peer_access() == 0
+    rows = 4099
+    shards = [torch.randint(0, 256, (rows, 96), dtype=torch.uint8, device="cuda:%d" % i) for i in range(n)]
+    outs = [torch.zeros((n * rows, 96), dtype=torch.uint8, device="cuda:%d" % i) for i in range(n)]
+    for i in range(n):
+        torch.cuda.synchronize(i)
+    for i, src in enumerate(shards):
+        with torch.cuda.device(i):
+            st = torch.cuda.Stream(device=i)
+            for o in outs:
+                vb.memcpy_d2d_async(o[i * rows:(i + 1) * rows], src, src.numel(), st)
+            st.synchronize()
+    want = torch.cat([t.cpu() for t in shards], dim=0)
+    for o in outs:
+        assert torch.equal(o.cpu(), want)
+    vb.memcpy_d2d_async(outs[0], shards[0], 0)  # zero bytes: a no-op
+    assert vb.lib.fec_memcpy_d2d_async(None, shards[0].data_ptr(), 16, None) == vb.FEC_ERR_ARG
+
+
 def test_bcast_stores_results_into_every_copy(vb, checker):
     """The *_bcast calls: the RS kernel stores its results into extra buffers as well -- on this device and, with
     peer access, on the others (the gather fused into the producing kernel)."""

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "fec_device_free": (None, [_vp]),
     "fec_memcpy_h2d": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "fec_memcpy_d2h": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "fec_memcpy_d2d_async": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
     "fec_device_synchronize": (ctypes.c_int, []),
     "fec_set_viterbi_kernel": (ctypes.c_int, [ctypes.c_int]),
     "fec_set_energy_dispersal": (ctypes.c_int, [ctypes.c_int]),
@@ -394,6 +395,13 @@ class PeerBuffer:
         self.local = None
         lib.fec_device_free(self.ptr)
         self.base, self.ptr = [], None
+
+
+def memcpy_d2d_async(dst, src, nbytes: int, stream=None):
+    """Copy-engine copy between device buffers (tensors or raw addresses; peers' buffers included) on `stream`."""
+    d = dst.data_ptr() if hasattr(dst, "data_ptr") else int(dst)
+    s_ = src.data_ptr() if hasattr(src, "data_ptr") else int(src)
+    _check(lib.fec_memcpy_d2d_async(d, s_, nbytes, _stream_ptr(stream)), "fec_memcpy_d2d_async")
 
 
 def _ptr_array(ptrs):

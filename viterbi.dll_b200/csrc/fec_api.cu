@@ -1472,6 +1472,14 @@ int fec_memcpy_d2h(void* dst, const void* d_src, size_t bytes) {
     return fail(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy D2H") ? FEC_ERR_DEVICE : FEC_OK;
 }
 
+// Device-to-device copy by the copy engines (peer buffers included: the gather of result arrays without a kernel).
+int fec_memcpy_d2d_async(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+    if (bytes == 0) return FEC_OK;
+    if (!d_dst || !d_src) return bad_arg("null pointer");
+    return fail(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream), "cudaMemcpyAsync D2D") ? FEC_ERR_DEVICE
+                                                                                                                     : FEC_OK;
+}
+
 int fec_device_synchronize(void) { return fail(cudaDeviceSynchronize(), "cudaDeviceSynchronize") ? FEC_ERR_DEVICE : FEC_OK; }
 
 int fec_set_energy_dispersal(int on) {
