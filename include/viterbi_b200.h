@@ -151,13 +151,16 @@ int fec_set_devices(const int* ordinals, int count);
 /* Copies up to `capacity` selected ordinals to `ordinals` (may be NULL) and returns how many are selected. */
 int fec_get_devices(int* ordinals, int capacity);
 
-/* The one collective of the design: gather device-resident result arrays over
- * NVLink with ncclAllGather, for hosts that keep the shards on the GPUs.  Single process, one communicator per
- * selected device (ncclCommInitAll on first use; NCCL is loaded at run time from libnccl.so.2 or
- * $VITERBI_B200_NCCL_LIB -- the library has no link-time dependency on it).  Shard i (bytes_per_shard bytes at
- * d_shard[i], resident on selected device i) arrives at offset i * bytes_per_shard of every d_all[j]
- * (each d_all[j] holds count * bytes_per_shard bytes on device j).  Enqueued on streams[i] (cudaStream_t of
- * device i; streams == NULL or an entry NULL = that device's default stream); the caller synchronises. */
+/* The one exchange of the design: gather device-resident result arrays over NVLink, for
+ * hosts that keep the shards on the GPUs.  Single process.  Shard i (bytes_per_shard bytes at d_shard[i], resident on
+ * selected device i) arrives at offset i * bytes_per_shard of every d_all[j] (each d_all[j] holds
+ * count * bytes_per_shard bytes on device j; d_shard[i] may be that very place in d_all[i]).  Enqueued on streams[i]
+ * (cudaStream_t of device i; streams == NULL or an entry NULL = that device's default stream); the result is
+ * complete once the caller has synchronised ALL of them.
+ * Default transport: the copy engines (cudaMemcpyPeerAsync, peer access enabled on first use) -- no kernel, no SM
+ * taken from the decoders, no dependency on NCCL.  VITERBI_B200_GATHER=nccl uses ncclAllGather instead (one
+ * communicator per selected device, ncclCommInitAll on first use; NCCL is loaded at run time from libnccl.so.2 or
+ * $VITERBI_B200_NCCL_LIB -- the library has no link-time dependency on it). */
 int fec_allgather_device(const void* const* d_shard, void* const* d_all, size_t bytes_per_shard, void* const* streams);
 
 /* Energy dispersal (ETSI EN 300 401 clause 10): a DAB transmitter XORs every logical frame with the PRBS of

@@ -178,15 +178,18 @@ def test_bcast_stores_results_into_every_copy(vb, checker):
 
 @pytest.mark.timeout(900)
 @pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
-def test_native_host_decodes_one_batch_on_all_devices(vb, tmp_path):
-    """tests/host/multi_device_check.cpp: a C++ host without torch, all GPUs of the box, bit-exact vs the checker."""
+@pytest.mark.parametrize("gather", ["dma", "nccl"])
+def test_native_host_decodes_one_batch_on_all_devices(vb, tmp_path, gather):
+    """tests/host/multi_device_check.cpp: a C++ host without torch, all GPUs of the box, bit-exact vs the checker;
+    once per transport of fec_allgather_device (copy engines, the default, and ncclAllGather)."""
     import oracle_lib
 
     chk = oracle_lib.checker()
     exe = tmp_path / "multi_device_check"
     subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-o", str(exe),
                     os.path.join(ROOT, "tests", "host", "multi_device_check.cpp"), "-ldl"], check=True)
-    run = subprocess.run([str(exe), vb.LIB_PATH, chk.lib._name, "16384"], capture_output=True, text=True)
+    run = subprocess.run([str(exe), vb.LIB_PATH, chk.lib._name, "16384"], capture_output=True, text=True,
+                         env=dict(os.environ, VITERBI_B200_GATHER=gather))
     assert run.returncode == 0, run.stdout + run.stderr
     rep = json.loads(run.stdout.strip().splitlines()[-1])
     assert rep["ok"] and rep["devices"] == vb.lib.fec_device_count()

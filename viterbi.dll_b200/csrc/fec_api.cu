@@ -1302,10 +1302,8 @@ int fec_set_devices(const int* ordinals, int count) {
     return FEC_OK;
 }
 
-int fec_enable_peer_access(void) {
-    std::lock_guard<std::mutex> lock(g_pool.mu);
-    std::vector<int> devs;
-    if (!selected_devices(devs)) return FEC_ERR_DEVICE;
+// cudaDeviceEnablePeerAccess between every pair of `devs` (pool mutex held)
+static int enable_peer_access_among(const std::vector<int>& devs) {
     int cur = -1;
     (void)cudaGetDevice(&cur);
     int rc = FEC_OK;
@@ -1328,6 +1326,13 @@ int fec_enable_peer_access(void) {
         }
     if (cur >= 0) (void)cudaSetDevice(cur);
     return rc;
+}
+
+int fec_enable_peer_access(void) {
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    std::vector<int> devs;
+    if (!selected_devices(devs)) return FEC_ERR_DEVICE;
+    return enable_peer_access_among(devs);
 }
 
 // ---- CUDA IPC: one process per GPU hosts map each other's result buffers, so that the *_bcast kernels can store
@@ -1389,9 +1394,36 @@ int fec_allgather_device(const void* const* d_shard, void* const* d_all, size_t 
     for (size_t i = 0; i < devs.size(); i++)
         if (!d_shard[i] || !d_all[i]) return bad_arg("null pointer");
     if (bytes_per_shard == 0) return FEC_OK;
-    if (!nccl_load()) return FEC_ERR_DEVICE;
     int cur = -1;
     (void)cudaGetDevice(&cur);
+    // Default: the copy engines push every shard into every device's array (cudaMemcpyPeerAsync over NVLink, no
+    // kernel, no dependency on NCCL).  VITERBI_B200_GATHER=nccl selects the collective instead.
+    static const bool use_nccl = [] {
+        const char* env = getenv("VITERBI_B200_GATHER");
+        return env && strcmp(env, "nccl") == 0;
+    }();
+    if (!use_nccl) {
+        static std::vector<int> peers_enabled_for;
+        if (peers_enabled_for != devs) {
+            (void)enable_peer_access_among(devs);  // best effort: without it the copies are staged through the host
+            t_error.clear();
+            peers_enabled_for = devs;
+        }
+        int rc = FEC_OK;
+        for (size_t i = 0; i < devs.size() && rc == FEC_OK; i++) {
+            if (fail(cudaSetDevice(devs[i]), "cudaSetDevice")) { rc = FEC_ERR_DEVICE; break; }
+            cudaStream_t st = streams ? (cudaStream_t)streams[i] : nullptr;
+            for (size_t j = 0; j < devs.size() && rc == FEC_OK; j++) {
+                uint8_t* dst = static_cast<uint8_t*>(d_all[j]) + i * bytes_per_shard;
+                if (dst == d_shard[i]) continue;  // in-place shard
+                if (fail(cudaMemcpyPeerAsync(dst, devs[j], d_shard[i], devs[i], bytes_per_shard, st), "cudaMemcpyPeerAsync"))
+                    rc = FEC_ERR_DEVICE;
+            }
+        }
+        if (cur >= 0) (void)cudaSetDevice(cur);
+        return rc;
+    }
+    if (!nccl_load()) return FEC_ERR_DEVICE;
     if (g_nccl.devs != devs) {
         for (ncclComm_t c : g_nccl.comms) g_nccl.CommDestroy(c);
         g_nccl.comms.assign(devs.size(), nullptr);
