@@ -1108,7 +1108,7 @@ int viterbi_deconvolve_batch_punctured_device(unsigned int framebits, const uint
     DeviceState* st = device_state();
     if (!st) return FEC_ERR_DEVICE;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t nsym = 4 * ((size_t)framebits + 6), nout = (framebits + 7) / 8;
+    const size_t nsym = 4 * ((size_t)framebits + 6);
     if (punct_fused() && uses_pair_kernel(n, framebits)) {
         // Fused path: the throughput kernel expands the rows in its symbol fetch.  Its fetch may touch up to
         // kPunctSlackBytes past a row, which for every row but the last one is simply the next row; the last row
