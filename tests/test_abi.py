@@ -135,3 +135,21 @@ def test_bench_reference_arm_runs_the_reference_code_only(tmp_path):
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert "libviterbi_ref" in out.stderr or "libfec_oracle" in out.stderr, "LD_DEBUG=files did not list the checker library"
     assert "libviterbi_b200.so" not in out.stderr, "the reference arm loaded the product library"
+
+
+def test_native_hosts_compile_against_the_header(tmp_path):
+    """The C++ hosts that only run on a GPU box (tests/host/multi_device_check.cpp, profiles/microbench/latbench.cpp)
+    must at least keep compiling here, so that a change of the C ABI cannot break them unnoticed."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        import pytest
+
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for src in (os.path.join(root, "tests", "host", "multi_device_check.cpp"),
+                os.path.join(root, "profiles", "microbench", "latbench.cpp")):
+        out = subprocess.run(["g++", "-std=c++17", "-O0", "-pthread", "-c", "-o", str(tmp_path / "x.o"), src],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, src + "\n" + out.stderr[-2000:]
